@@ -1,0 +1,163 @@
+// Developer probe (not part of the library): validates the tcgen05 skinny products against a CPU
+// double-precision reference for every operand-layout variant, then times them on a large matrix.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o umma_probe umma_probe.cu
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <string>
+#include "../umma_skinny.cuh"
+#include "../tmap.h"
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);  \
+      exit(2);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+using namespace fz;
+
+static uint32_t rng_state = 12345u;
+static float frand() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return (rng_state >> 8) * (1.0f / 16777216.0f);
+}
+
+template <int N, bool T>
+static void launch(const CUtensorMap& tx, const CUtensorMap& tg, SkinnyParams p, int ksplit, cudaStream_t st) {
+  using Cfg = SkinnyCfg<N>;
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(umma_skinny_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr = true;
+  }
+  dim3 grid((p.M + kSkBM - 1) / kSkBM, ksplit);
+  umma_skinny_kernel<N, T><<<grid, kSkThreads, Cfg::kSmemBytes, st>>>(tx, tg, p);
+}
+
+static void dispatch(int N, bool T, const CUtensorMap& tx, const CUtensorMap& tg, SkinnyParams p, int ksplit,
+                     cudaStream_t st) {
+  if (N == 64 && !T) launch<64, false>(tx, tg, p, ksplit, st);
+  else if (N == 64 && T) launch<64, true>(tx, tg, p, ksplit, st);
+  else if (N == 128 && !T) launch<128, false>(tx, tg, p, ksplit, st);
+  else if (N == 128 && T) launch<128, true>(tx, tg, p, ksplit, st);
+  else if (N == 192 && !T) launch<192, false>(tx, tg, p, ksplit, st);
+  else if (N == 192 && T) launch<192, true>(tx, tg, p, ksplit, st);
+  else { printf("bad N\n"); exit(2); }
+}
+
+// returns max relative error (vs max |ref|)
+static double run_case(int rows, int cols, int k, int terms, bool trans, int ksplit, bool verbose) {
+  const int kp = 64, N = terms * kp;
+  const int ld = (cols + 7) / 8 * 8;
+  const int M = trans ? cols : rows;       // rows of C
+  const int K = trans ? rows : cols;       // reduction
+  const int ng = K;                        // rows of Gs
+  std::vector<__nv_bfloat16> hX((size_t)rows * ld), hG((size_t)ng * N);
+  std::vector<float> fX((size_t)rows * ld), fG((size_t)ng * N);
+  for (size_t i = 0; i < hX.size(); ++i) { hX[i] = __float2bfloat16(frand() - 0.3f); fX[i] = __bfloat162float(hX[i]); }
+  for (int r = 0; r < ng; ++r)
+    for (int c = 0; c < N; ++c) {
+      int q = c % kp;
+      float v = (q < k) ? (frand() - 0.5f) * ((c / kp) == 0 ? 1.f : 0.004f) : 0.f;
+      hG[(size_t)r * N + c] = __float2bfloat16(v);
+      fG[(size_t)r * N + c] = __bfloat162float(hG[(size_t)r * N + c]);
+    }
+  __nv_bfloat16 *dX, *dG; float* dC;
+  CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dG, hG.size() * 2));
+  CK(cudaMalloc(&dC, (size_t)M * k * 4));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dG, hG.data(), hG.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dC, 0, (size_t)M * k * 4));
+  CUtensorMap tx, tg; std::string err;
+  bool ok = trans ? make_tmap_bf16_2d(&tx, dX, rows, cols, ld, 64, 64, &err)
+                  : make_tmap_bf16_2d(&tx, dX, rows, cols, ld, 64, 128, &err);
+  ok = ok && make_tmap_bf16_2d(&tg, dG, ng, N, N, 64, 64, &err);
+  if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
+  SkinnyParams p;
+  p.C = dC; p.ldc = k; p.rows_per_chunk = 1ll << 40; p.chunk_stride = 0; p.M = M; p.K = K; p.k = k; p.kp = kp;
+  p.terms = terms;
+  int kps = ((K + ksplit - 1) / ksplit + 63) / 64 * 64;
+  int eff_split = (K + kps - 1) / kps;
+  p.k_per_split = kps; p.atomic = eff_split > 1;
+  dispatch(N, trans, tx, tg, p, eff_split, 0);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hC((size_t)M * k);
+  CK(cudaMemcpy(hC.data(), dC, hC.size() * 4, cudaMemcpyDeviceToHost));
+  double maxref = 0, maxerr = 0;
+  for (int m = 0; m < M; ++m)
+    for (int q = 0; q < k; ++q) {
+      double s = 0;
+      for (int kk = 0; kk < K; ++kk) {
+        double x = trans ? fX[(size_t)kk * ld + m] : fX[(size_t)m * ld + kk];
+        double g = 0;
+        for (int t = 0; t < terms; ++t) g += fG[(size_t)kk * N + t * kp + q];
+        s += x * g;
+      }
+      maxref = fmax(maxref, fabs(s));
+      maxerr = fmax(maxerr, fabs(s - hC[(size_t)m * k + q]));
+    }
+  if (verbose)
+    printf("case rows=%d cols=%d k=%d terms=%d trans=%d ksplit=%d : max|ref|=%.4g max err=%.3g rel=%.3g %s\n", rows,
+           cols, k, terms, (int)trans, eff_split, maxref, maxerr, maxerr / maxref,
+           (maxerr / maxref < 2e-5) ? "OK" : "FAIL");
+  cudaFree(dX); cudaFree(dG); cudaFree(dC);
+  return maxerr / maxref;
+}
+
+static void bench(int n, int terms, bool trans) {
+  const int kp = 64, N = terms * kp, k = 64;
+  size_t elems = (size_t)n * n;
+  __nv_bfloat16 *dX, *dG; float* dC;
+  CK(cudaMalloc(&dX, elems * 2)); CK(cudaMalloc(&dG, (size_t)n * N * 2)); CK(cudaMalloc(&dC, (size_t)n * k * 4));
+  CK(cudaMemset(dX, 0x3c, elems * 2));  // bf16 0x3c3c ~ 0.0115
+  CK(cudaMemset(dG, 0x3c, (size_t)n * N * 2));
+  CUtensorMap tx, tg; std::string err;
+  bool ok = trans ? make_tmap_bf16_2d(&tx, dX, n, n, n, 64, 64, &err) : make_tmap_bf16_2d(&tx, dX, n, n, n, 64, 128, &err);
+  ok = ok && make_tmap_bf16_2d(&tg, dG, n, N, N, 64, 64, &err);
+  if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
+  for (int ksplit : {1, 2, 4}) {
+    SkinnyParams p;
+    p.C = dC; p.ldc = k; p.rows_per_chunk = 1ll << 40; p.chunk_stride = 0; p.M = n; p.K = n; p.k = k; p.kp = kp;
+    p.terms = terms;
+    int kps = ((n + ksplit - 1) / ksplit + 63) / 64 * 64;
+    p.k_per_split = kps; p.atomic = ksplit > 1;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 2; ++w) dispatch(N, trans, tx, tg, p, ksplit, 0);
+    CK(cudaDeviceSynchronize());
+    const int reps = 5;
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) dispatch(N, trans, tx, tg, p, ksplit, 0);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+    double gb = elems * 2.0 / 1e9;
+    printf("bench n=%d terms=%d trans=%d ksplit=%d : %.3f ms  %.1f GB/s (R bytes only)  %.1f TFLOP/s\n", n, terms,
+           (int)trans, ksplit, ms, gb / (ms * 1e-3), 2.0 * elems * N / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(dX); cudaFree(dG); cudaFree(dC);
+}
+
+int main(int argc, char** argv) {
+  int nbench = argc > 1 ? atoi(argv[1]) : 32768;
+  int fails = 0;
+  for (int trans = 0; trans < 2; ++trans)
+    for (int terms = 1; terms <= 3; ++terms) {
+      fails += run_case(256, 256, 64, terms, trans, 1, true) > 2e-5;
+      fails += run_case(1000, 520, 64, terms, trans, 1, true) > 2e-5;
+      fails += run_case(520, 1000, 50, terms, trans, 3, true) > 2e-5;
+      fails += run_case(130, 77, 7, terms, trans, 1, true) > 2e-5;
+    }
+  fails += run_case(2048, 4096, 64, 2, false, 4, true) > 2e-5;
+  fails += run_case(4096, 2048, 64, 2, true, 4, true) > 2e-5;
+  printf("correctness: %d failing cases\n", fails);
+  if (nbench > 0) {
+    for (int trans = 0; trans < 2; ++trans)
+      for (int terms = 1; terms <= 2; ++terms) bench(nbench, terms, trans);
+  }
+  return fails ? 1 : 0;
+}

@@ -1,0 +1,73 @@
+"""Seeded problem definitions shared by make_golden.py (reference side) and the parity tests.
+
+Every case is rebuilt deterministically from numpy RandomState seeds, so the committed fixture only
+has to hold the reference's *outputs* (initial factors and trajectory snapshots).  Shapes follow the
+reference's own README / unit tests: README 3-type graph (README.md:49-70), parallel relations
+(tests/test_multiple_relations.py), rank > n_objects (tests/test_base.py:16-17), masks
+(tests/test_dfmc.py:25-39), constraint matrices (datasets/base.py:45-61 dicty ppi in [-0.1, 0]).
+"""
+import numpy as np
+
+
+class Tag(object):
+    """Minimal stand-in for an object type where identity matters (transform uses ``is``)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return str(self.name)
+
+
+def _sparse_sym_constraint(rs, n, density=0.1, scale=0.1):
+    th = (rs.rand(n, n) < density) * (rs.rand(n, n) - 0.8) * scale
+    return (th + th.T) / 2
+
+
+def fit_cases():
+    c = {}
+
+    rs = np.random.RandomState(100)
+    c["readme3"] = dict(
+        algo="dfmf", types=["t1", "t2", "t3"], ranks={"t1": 10, "t2": 20, "t3": 30},
+        R={("t1", "t2"): [rs.rand(50, 100)], ("t1", "t3"): [rs.rand(50, 40)], ("t2", "t3"): [rs.rand(100, 40)]},
+        Theta={}, M=None, init_type="random_c", seed=0, max_iter=50, snapshots=[0, 9, 49])
+
+    rs = np.random.RandomState(101)
+    c["multi_theta"] = dict(
+        algo="dfmf", types=["a", "b", "c"], ranks={"a": 10, "b": 20, "c": 30},
+        R={("a", "b"): [rs.rand(50, 100), rs.rand(50, 100) - 0.2], ("a", "c"): [rs.rand(50, 40)],
+           ("c", "b"): [rs.rand(40, 100)]},
+        Theta={("a", "a"): [_sparse_sym_constraint(rs, 50)], ("b", "b"): [_sparse_sym_constraint(rs, 100),
+                                                                      _sparse_sym_constraint(rs, 100)]},
+        M=None, init_type="random_vcol", seed=3, max_iter=50, snapshots=[0, 9, 49])
+
+    rs = np.random.RandomState(102)
+    c["rank_gt_n"] = dict(
+        algo="dfmf", types=["t1", "t2", "t3"], ranks={"t1": 30, "t2": 40, "t3": 40},
+        R={("t1", "t2"): [rs.rand(50, 30)], ("t1", "t3"): [rs.rand(50, 40)], ("t2", "t3"): [rs.rand(30, 40)]},
+        Theta={}, M=None, init_type="random", seed=1, max_iter=30, snapshots=[0, 9, 29])
+
+    rs = np.random.RandomState(103)
+    Rm = {("u", "m"): [rs.rand(60, 80) * 5], ("m", "g"): [(rs.rand(80, 12) < 0.2).astype(float)],
+          ("m", "a"): [(rs.rand(80, 70) < 0.1).astype(float), rs.rand(80, 70)]}
+    c["completion"] = dict(
+        algo="dfmc", types=["u", "m", "g", "a"], ranks={"u": 8, "m": 12, "g": 4, "a": 10},
+        R=Rm, Theta={("u", "u"): [_sparse_sym_constraint(rs, 60)]},
+        M={("u", "m"): [rs.rand(60, 80) > 0.3], ("m", "g"): [None], ("m", "a"): [None, rs.rand(80, 70) > 0.8]},
+        init_type="random_vcol", seed=5, max_iter=40, snapshots=[0, 9, 39])
+    return c
+
+
+def transform_cases():
+    c = {}
+    rs = np.random.RandomState(200)
+    c["project_rows"] = dict(fit="readme3", target="t1",
+                             R_new={("t1", "t2"): [rs.rand(10, 100)], ("t1", "t3"): [rs.rand(10, 40)]},
+                             Theta={}, init_type="random_c", seed=11, max_iter=60, snapshots=[0, 9, 59])
+    rs = np.random.RandomState(201)
+    c["project_cols"] = dict(fit="readme3", target="t3",
+                             R_new={("t1", "t3"): [rs.rand(50, 9)], ("t2", "t3"): [rs.rand(100, 9)]},
+                             Theta={("t3", "t3"): [_sparse_sym_constraint(rs, 9, 0.5, 0.05)]},
+                             init_type="random", seed=12, max_iter=60, snapshots=[0, 9, 59])
+    return c
