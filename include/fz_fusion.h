@@ -1,0 +1,112 @@
+/* fz_fusion.h -- C ABI of the B200-native collective matrix tri-factorization engine.
+ *
+ * The reference (mims-harvard/scikit-fusion @ 88dd02c) has no FFI; its seam is three Python free
+ * functions called by keyword from the estimator classes:
+ *     dfmf(R, Theta, obj_types, obj_type2rank, ...)            skfusion/fusion/decomposition/_dfmf.py:127
+ *     dfmc(R, M, Theta, obj_types, obj_type2rank, ...)         skfusion/fusion/decomposition/_dfmc.py:181
+ *     transform(R_ij, Theta_i, target, ranks, G, S, ...)       skfusion/fusion/decomposition/_dfmf.py:330
+ * This header is what a binding for that seam binds (ctypes stub in INTEGRATION.md).  One engine
+ * handle == one call of one of those functions: describe the block structure (object types,
+ * relation / constraint matrices, masks), hand over the initial factors, run N iterations of the
+ * multiplicative-update loop on the GPU, read the factors G_t and backbones S_ij back.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative fz_status otherwise; fz_last_error() gives text.
+ *     No exception crosses the ABI.  A handle is not thread-safe; distinct handles are independent.
+ *   - matrices are row-major; `ld` is the leading dimension in ELEMENTS.
+ *   - `mem` says where a caller buffer lives (FZ_HOST / FZ_DEVICE).  Inputs are copied (and converted
+ *     to the storage dtype) unless `borrow` is set, in which case the device pointer must stay valid
+ *     and unmodified for the lifetime of the handle (dfmc never borrows: it rewrites masked entries,
+ *     _dfmc.py:268).  Outputs are written into caller-owned buffers.
+ *   - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*; NULL =
+ *     the legacy default stream).  Calls that return data to the HOST synchronise that stream.
+ *   - row sharding (one process per GPU): fz_set_shard(world, rank) before any fz_add_type.  Type t
+ *     then owns rows [rank*m_t, (rank+1)*m_t) with m_t = ceil(n_t/world); relation (i,j) is given as
+ *     the row block of type i's local rows; the iteration is split into fz_phase_* calls and the
+ *     caller runs the collectives between them on the buffers fz_comm_* exposes.
+ */
+#ifndef FZ_FUSION_H
+#define FZ_FUSION_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fz_engine fz_engine;
+
+typedef enum { FZ_F64 = 0, FZ_F32 = 1, FZ_BF16 = 2, FZ_U8 = 3 } fz_dtype;
+typedef enum { FZ_HOST = 0, FZ_DEVICE = 1 } fz_mem;
+typedef enum { FZ_DFMF = 0, FZ_DFMC = 1 } fz_algo;
+
+typedef enum {
+  FZ_OK = 0,
+  FZ_ERR_INVALID = -1,     /* bad argument / call order            */
+  FZ_ERR_CUDA = -2,        /* CUDA runtime or driver error         */
+  FZ_ERR_UNSUPPORTED = -3, /* combination not implemented          */
+  FZ_ERR_NOMEM = -4
+} fz_status;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* compute = FZ_F32 (fp32 factors + products, fp64 k x k chain) or FZ_F64 (all fp64, parity mode). */
+int fz_create(fz_engine** out, int device, int compute);
+int fz_destroy(fz_engine* e);
+const char* fz_last_error(const fz_engine* e); /* e may be NULL: error of the last failed fz_create */
+int fz_version(void);
+/* number of engine kernels launched so far on this handle (bench.py's gpu_launches) */
+int64_t fz_launch_count(const fz_engine* e);
+
+/* ---- problem description (reference: the R / Theta / M dicts, dfmf.py:69-85, dfmc.py:69-94) ---- */
+int fz_set_shard(fz_engine* e, int world, int rank);
+/* returns the type id (>= 0).  n = number of objects (global), k = factorization rank. */
+int fz_add_type(fz_engine* e, int64_t n, int k);
+/* Relation between row type ti and column type tj; ti == tj declares a constraint matrix Theta_t.
+ *   data        rows_local x n_tj matrix of `src` dtype (rows_local = n_ti unless sharded)
+ *   storage     dtype kept on the device: FZ_F64 / FZ_F32 (SIMT fp path) or FZ_BF16 (tensor-core path,
+ *               needs ld % 8 == 0 when borrowed; the engine pads its own copies)
+ *   mask        optional rows_local x n_tj uint8 (non-zero = unknown entry, dfmc), NULL otherwise
+ * returns the relation id (>= 0), in insertion order. */
+int fz_add_relation(fz_engine* e, int ti, int tj, const void* data, int64_t ld, int src, int mem, int storage,
+                    int borrow, const uint8_t* mask, int64_t mask_ld, int mask_mem);
+/* Initial factor G_t (n_t x k_t, global rows).  Reference: initialize(), _init.py:6-61 (host side). */
+int fz_set_factor(fz_engine* e, int t, const void* G0, int64_t ld, int src, int mem);
+/* Frozen backbone S_ij for transform (k_ti x k_tj).  Reference: dfmf.py:112-114. */
+int fz_set_backbone(fz_engine* e, int rel, const void* S, int64_t ld, int src, int mem);
+/* number of bf16 split terms used for factors on the tensor-core path (1..3, default 2) */
+int fz_set_split_terms(fz_engine* e, int terms);
+/* allocate workspaces, build TMA descriptors; must precede the calls below */
+int fz_finalize(fz_engine* e);
+
+/* ---- the hot loop --------------------------------------------------------------------------- */
+/* n_iters iterations of the multiplicative-update loop (_dfmf.py:212-296 / _dfmc.py:270-366).
+ * Unsharded handles only (sharded handles use the phases below). */
+int fz_iterate(fz_engine* e, int algo, int n_iters, void* stream);
+/* Sharded iteration, in order:  products -> [all-reduce small, reduce-scatter B] -> update ->
+ * [all-gather factors].  fz_iterate == products + update when world == 1. */
+int fz_phase_products(fz_engine* e, int algo, void* stream);
+int fz_phase_update(fz_engine* e, int algo, void* stream);
+/* communication buffers (device pointers, valid after fz_finalize) */
+int fz_comm_small(fz_engine* e, void** ptr, int64_t* count_f64);               /* all-reduce, fp64 */
+int fz_comm_bpartial(fz_engine* e, int rel, void** full_ptr, void** local_ptr, /* reduce-scatter  */
+                     int64_t* local_count, int* dtype);
+int fz_comm_factor(fz_engine* e, int t, void** full_ptr, int64_t* local_count, int* dtype); /* all-gather */
+
+/* online projection (_dfmf.py:330-458): only `target` moves; other factors and all backbones frozen.
+ * fz_transform_prepare computes the loop-invariant terms once; fz_transform_iterate runs the loop. */
+int fz_transform_prepare(fz_engine* e, int target, void* stream);
+int fz_transform_iterate(fz_engine* e, int n_iters, void* stream);
+
+/* ---- results --------------------------------------------------------------------------------- */
+int fz_get_factor(fz_engine* e, int t, void* dst, int64_t ld, int dst_dtype, int mem, void* stream);
+int fz_get_backbone(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int mem, void* stream);
+/* Frobenius residuals ||R - G_i S G_j^T||_F per relation (un-squared, _dfmf.py:306-319) and their sum,
+ * with the current factors and the backbones of the last iteration.  per_relation may be NULL. */
+int fz_objective(fz_engine* e, double* per_relation, double* total, void* stream);
+/* completed relation G_i S_ij G_j^T (base.py:119-146) into a caller buffer */
+int fz_complete(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int mem, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FZ_FUSION_H */

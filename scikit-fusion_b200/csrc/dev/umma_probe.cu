@@ -79,7 +79,7 @@ static double run_case(int rows, int cols, int k, int terms, bool trans, int ksp
   ok = ok && make_tmap_bf16_2d(&tg, dG, ng, N, N, 64, 64, &err);
   if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
   SkinnyParams p;
-  p.C = dC; p.ldc = k; p.rows_per_chunk = 1ll << 40; p.chunk_stride = 0; p.M = M; p.K = K; p.k = k; p.kp = kp;
+  p.C = dC; p.ldc = k; p.g_row0 = 0; p.M = M; p.K = K; p.k = k; p.kp = kp;
   p.terms = terms;
   int kps = ((K + ksplit - 1) / ksplit + 63) / 64 * 64;
   int eff_split = (K + kps - 1) / kps;
@@ -123,7 +123,7 @@ static void bench(int n, int terms, bool trans) {
   if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
   for (int ksplit : {1, 2, 4}) {
     SkinnyParams p;
-    p.C = dC; p.ldc = k; p.rows_per_chunk = 1ll << 40; p.chunk_stride = 0; p.M = n; p.K = n; p.k = k; p.kp = kp;
+    p.C = dC; p.ldc = k; p.g_row0 = 0; p.M = n; p.K = n; p.k = k; p.kp = kp;
     p.terms = terms;
     int kps = ((n + ksplit - 1) / ksplit + 63) / 64 * 64;
     p.k_per_split = kps; p.atomic = ksplit > 1;

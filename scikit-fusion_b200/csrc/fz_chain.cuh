@@ -1,0 +1,291 @@
+// The fp64 "small chain" of one DFMF iteration: everything that is k x k.
+//   pinv_spd        P_t = pinv(nan_to_num(G_t^T G_t))                         (reference _dfmf.py:228-232)
+//   backbone_chain  S_ij = P_i (G_i^T R_ij G_j) P_j ; S G^T G S^T terms       (reference _dfmf.py:236-239, 260, 272)
+//   type_sums       per-type sums of the +/- parts of those k x k terms       (reference _dfmf.py:278-282)
+// The reference gets P from scipy.linalg.pinv (SVD, cutoff max(M,N)*eps*sigma_max).  Here: Cholesky
+// inverse when the Gram matrix is safely positive definite, otherwise a one-sided Jacobi eigen-solve
+// with the same cutoff rule -- both in fp64, one CTA per matrix, matrices in global/L2 memory so any
+// rank works.  SURVEY F7 explains why this chain cannot be fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fz_kernels.cuh"
+
+namespace fz {
+
+constexpr int kChainThreads = 512;
+
+// C[m x n] = op(A) * op(B), all row-major fp64; executed by the whole block; caller syncs afterwards.
+__device__ __forceinline__ void block_mm(double* C, int ldc, const double* A, int lda, bool ta, const double* B, int ldb,
+                                         bool tb, int m, int n, int kk) {
+  for (int o = threadIdx.x; o < m * n; o += blockDim.x) {
+    const int i = o / n, j = o % n;
+    double s = 0.0;
+    for (int c = 0; c < kk; ++c) {
+      const double a = ta ? A[(long long)c * lda + i] : A[(long long)i * lda + c];
+      const double b = tb ? B[(long long)j * ldb + c] : B[(long long)c * ldb + j];
+      s += a * b;
+    }
+    C[(long long)i * ldc + j] = s;
+  }
+}
+
+struct PinvJob {
+  const double* gram_raw;  // k x k (sum over chunks / ranks), not yet scrubbed
+  double* gram;            // k x k scrubbed copy kept for the backbone chain
+  double* P;               // k x k output
+  double* work;            // 3 * k * k doubles
+  int* info;               // [0] = 0 Cholesky, 1 Jacobi ; [1] = numerical rank
+  int k;
+};
+
+__global__ void __launch_bounds__(kChainThreads)
+pinv_spd(const PinvJob* __restrict__ jobs) {
+  const PinvJob job = jobs[blockIdx.x];
+  const int k = job.k;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  double* L = job.work;                 // k x k
+  double* X = job.work + (long long)k * k;      // k x k
+  double* V = job.work + 2ll * k * k;           // k x k (Jacobi)
+  __shared__ double s_maxdiag;
+  __shared__ int s_fail;
+  __shared__ int s_rot;
+  __shared__ double s_smax;
+
+  for (int o = tid; o < k * k; o += nth) {
+    const double v = scrub(job.gram_raw[o]);
+    job.gram[o] = v;
+    L[o] = v;
+  }
+  if (tid == 0) { s_fail = 0; s_maxdiag = 0.0; }
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int i = 0; i < k; ++i) m = fmax(m, fabs(L[(long long)i * k + i]));
+    s_maxdiag = m;
+    if (!(m > 0.0) || !(m < 1e300)) s_fail = 1;
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- Cholesky (right-looking)
+  if (!s_fail) {
+    const double tol = 1e-10 * s_maxdiag;
+    for (int j = 0; j < k; ++j) {
+      if (tid == 0) {
+        const double d = L[(long long)j * k + j];
+        if (!(d > tol)) s_fail = 1;
+        else L[(long long)j * k + j] = sqrt(d);
+      }
+      __syncthreads();
+      if (s_fail) break;
+      const double dj = L[(long long)j * k + j];
+      for (int i = j + 1 + tid; i < k; i += nth) L[(long long)i * k + j] /= dj;
+      __syncthreads();
+      const int rem = k - j - 1;
+      for (int o = tid; o < rem * rem; o += nth) {
+        const int i = j + 1 + o / rem, c = j + 1 + o % rem;
+        if (c <= i) L[(long long)i * k + c] -= L[(long long)i * k + j] * L[(long long)c * k + j];
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (!s_fail) {
+    // X = L^{-1} (lower triangular), one column per thread
+    for (int j = tid; j < k; j += nth) {
+      for (int i = 0; i < j; ++i) X[(long long)i * k + j] = 0.0;
+      for (int i = j; i < k; ++i) {
+        double s = (i == j) ? 1.0 : 0.0;
+        for (int c = j; c < i; ++c) s -= L[(long long)i * k + c] * X[(long long)c * k + j];
+        X[(long long)i * k + j] = s / L[(long long)i * k + i];
+      }
+    }
+    __syncthreads();
+    // P = X^T X
+    for (int o = tid; o < k * k; o += nth) {
+      const int a = o / k, b = o % k;
+      double s = 0.0;
+      for (int i = max(a, b); i < k; ++i) s += X[(long long)i * k + a] * X[(long long)i * k + b];
+      job.P[o] = s;
+    }
+    if (tid == 0) { job.info[0] = 0; job.info[1] = k; }
+    return;
+  }
+
+  // ---------------------------------------------------------------- one-sided Jacobi on the rows of W = A
+  // (A symmetric: rows == columns).  After convergence row p of W is (A v_p)^T with v_p = row p of V,
+  // sigma_p = |row p|, and pinv(A) = sum_{sigma_p > cutoff} v_p (A v_p)^T / sigma_p^2.
+  double* W = L;
+  for (int o = tid; o < k * k; o += nth) {
+    W[o] = job.gram[o];
+    V[o] = (o / k == o % k) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+  const int kk = (k + 1) & ~1;            // players (dummy when k is odd)
+  const int npairs = kk / 2;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int round = 0; round < kk - 1; ++round) {
+      for (int pi = warp; pi < npairs; pi += nwarps) {
+        int p, q;
+        if (pi == 0) { p = kk - 1; q = round; }
+        else {
+          p = (round + pi) % (kk - 1);
+          q = (round - pi + (kk - 1)) % (kk - 1);
+        }
+        if (p >= k || q >= k) continue;
+        if (p > q) { const int t = p; p = q; q = t; }
+        double* wp = W + (long long)p * k;
+        double* wq = W + (long long)q * k;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int c = lane; c < k; c += 32) {
+          const double a = wp[c], b = wq[c];
+          al += a * a; be += b * b; ga += a * b;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, off);
+          be += __shfl_xor_sync(0xffffffffu, be, off);
+          ga += __shfl_xor_sync(0xffffffffu, ga, off);
+        }
+        if (fabs(ga) > 1e-15 * sqrt(al * be) && fabs(ga) > 0.0) {
+          const double zeta = (be - al) / (2.0 * ga);
+          const double t = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          double* vp = V + (long long)p * k;
+          double* vq = V + (long long)q * k;
+          for (int c = lane; c < k; c += 32) {
+            const double a = wp[c], b = wq[c];
+            wp[c] = cs * a - sn * b;
+            wq[c] = sn * a + cs * b;
+            const double x = vp[c], y = vq[c];
+            vp[c] = cs * x - sn * y;
+            vq[c] = sn * x + cs * y;
+          }
+          if (lane == 0) atomicAdd(&s_rot, 1);
+        }
+      }
+      __syncthreads();
+    }
+    if (s_rot == 0) break;
+    __syncthreads();
+  }
+  // sigma_p^2 into X[p], sigma_max
+  for (int p = tid; p < k; p += nth) {
+    double s = 0.0;
+    for (int c = 0; c < k; ++c) s += W[(long long)p * k + c] * W[(long long)p * k + c];
+    X[p] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int p = 0; p < k; ++p) m = fmax(m, X[p]);
+    s_smax = sqrt(m);
+    const double cut = (double)k * 2.220446049250313e-16 * s_smax;
+    int rank = 0;
+    for (int p = 0; p < k; ++p) rank += (sqrt(X[p]) > cut);
+    job.info[0] = 1;
+    job.info[1] = rank;
+  }
+  __syncthreads();
+  const double cutoff = (double)k * 2.220446049250313e-16 * s_smax;
+  for (int o = tid; o < k * k; o += nth) {
+    const int a = o / k, b = o % k;
+    double s = 0.0;
+    for (int p = 0; p < k; ++p) {
+      const double s2 = X[p];
+      if (sqrt(s2) > cutoff) s += V[(long long)p * k + a] * W[(long long)p * k + b] / s2;
+    }
+    job.P[o] = s;
+  }
+}
+
+template <class T>
+struct BackboneJob {
+  const double* M_raw;   // k_i x k_j  = G_i^T R_ij G_j  (summed over chunks / ranks)
+  const double* P_i;
+  const double* P_j;
+  const double* gram_i;
+  const double* gram_j;
+  double* S;             // k_i x k_j
+  double* t2;            // k_i x k_i  = S G_j^T G_j S^T
+  double* t5;            // k_j x k_j  = S^T G_i^T G_i S
+  T* W1;                 // k_j x k_i  = S^T in the compute dtype  (tmp1 = A S^T)
+  T* W4;                 // k_i x k_j  = S                         (tmp4 = B S)
+  double* work;          // 2 * max(k_i,k_j)^2
+  int ki, kj;
+  int solve;             // 1: compute S from M_raw; 0: S is given (transform)
+  int scrub;             // dfmf: nan_to_num on every k x k product
+};
+
+template <class T>
+__global__ void __launch_bounds__(kChainThreads)
+backbone_chain(const BackboneJob<T>* __restrict__ jobs) {
+  const BackboneJob<T> job = jobs[blockIdx.x];
+  const int ki = job.ki, kj = job.kj;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int km = max(ki, kj);
+  double* U = job.work;
+  double* Vw = job.work + (long long)km * km;
+  if (job.solve) {
+    // Vw = scrub(M) ; U = Vw * P_j ; S = scrub(P_i * U)
+    for (int o = tid; o < ki * kj; o += nth) Vw[o] = scrub(job.M_raw[o]);
+    __syncthreads();
+    block_mm(U, kj, Vw, kj, false, job.P_j, kj, false, ki, kj, kj);
+    __syncthreads();
+    block_mm(job.S, kj, job.P_i, ki, false, U, kj, false, ki, kj, ki);
+    __syncthreads();
+    for (int o = tid; o < ki * kj; o += nth) job.S[o] = scrub(job.S[o]);
+    __syncthreads();
+  }
+  // t2 = S gram_j S^T
+  block_mm(U, kj, job.S, kj, false, job.gram_j, kj, false, ki, kj, kj);
+  __syncthreads();
+  block_mm(job.t2, ki, U, kj, false, job.S, kj, true, ki, ki, kj);
+  __syncthreads();
+  // t5 = S^T gram_i S
+  block_mm(U, ki, job.S, kj, true, job.gram_i, ki, false, kj, ki, ki);
+  __syncthreads();
+  block_mm(job.t5, kj, U, ki, false, job.S, kj, false, kj, kj, ki);
+  __syncthreads();
+  if (job.scrub) {
+    for (int o = tid; o < ki * ki; o += nth) job.t2[o] = scrub(job.t2[o]);
+    for (int o = tid; o < kj * kj; o += nth) job.t5[o] = scrub(job.t5[o]);
+  }
+  for (int o = tid; o < ki * kj; o += nth) {
+    const int a = o / kj, b = o % kj;
+    const double s = job.S[o];
+    job.W4[o] = (T)s;
+    job.W1[(long long)b * ki + a] = (T)s;
+  }
+}
+
+template <class T>
+struct TypeSumJob {
+  const double* const* mats;  // n_mats pointers to k x k matrices (t2 of row-role relations, t5 of column-role ones)
+  T* Nsum;                    // k x k : sum of magnitudes of negative parts  (feeds the numerator)
+  T* Dsum;                    // k x k : sum of positive parts                (feeds the denominator)
+  int n_mats;
+  int k;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256)
+type_sums(const TypeSumJob<T>* __restrict__ jobs) {
+  const TypeSumJob<T> job = jobs[blockIdx.x];
+  for (int o = threadIdx.x; o < job.k * job.k; o += blockDim.x) {
+    double n = 0.0, d = 0.0;
+    for (int m = 0; m < job.n_mats; ++m) {
+      double p, q;
+      sign_split(job.mats[m][o], p, q);
+      d += p;
+      n += q;
+    }
+    job.Nsum[o] = (T)n;
+    job.Dsum[o] = (T)d;
+  }
+}
+
+}  // namespace fz

@@ -1,0 +1,1090 @@
+// B200-native collective matrix tri-factorization engine behind include/fz_fusion.h.
+//
+// One handle = one call of the reference's dfmf() / dfmc() / transform()
+// (skfusion/fusion/decomposition/_dfmf.py:127, _dfmc.py:181, _dfmf.py:330).  The per-iteration work is
+// regrouped around two streamed products per relation,
+//        A_ij = R_ij G_j          B_ij = R_ij^T G_i ,
+// from which everything the reference computes follows with k x k algebra:
+//        G_i^T R_ij G_j = G_i^T A_ij                     (S-update,  _dfmf.py:236-239)
+//        tmp1 = R_ij (G_j S^T) = A_ij S^T                 (_dfmf.py:254)
+//        tmp4 = R_ij^T (G_i S) = B_ij S                   (_dfmf.py:266)
+// bf16-stored relations take the tcgen05/TMA kernel (umma_skinny.cuh); fp32 / fp64-stored ones the exact
+// CUDA-core kernel.  The k x k chain is always fp64 (fz_chain.cuh).  There is no CPU fallback anywhere.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/fz_fusion.h"
+#include "fz_chain.cuh"
+#include "fz_kernels.cuh"
+#include "tmap.h"
+#include "umma_skinny.cuh"
+
+namespace fz {
+
+struct FzError {
+  int status;
+  std::string msg;
+};
+#define FZ_THROW(st, ...)                              \
+  do {                                                 \
+    char buf_[512];                                    \
+    snprintf(buf_, sizeof(buf_), __VA_ARGS__);         \
+    throw FzError{(st), std::string(buf_)};            \
+  } while (0)
+#define CUDA_OK(x)                                                                                 \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) FZ_THROW(FZ_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  void alloc(size_t n, bool zero = true) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      FZ_THROW(FZ_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+    }
+    bytes = n;
+    if (zero) CUDA_OK(cudaMemset(p, 0, n));
+  }
+  template <class U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+static inline size_t dtype_size(int d) {
+  switch (d) {
+    case FZ_F64: return 8;
+    case FZ_F32: return 4;
+    case FZ_BF16: return 2;
+    case FZ_U8: return 1;
+  }
+  return 0;
+}
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+class EngineBase {
+ public:
+  virtual ~EngineBase() {}
+  std::string err;
+  int64_t launches = 0;
+  virtual int compute_dtype() const = 0;
+  virtual void set_shard(int world, int rank) = 0;
+  virtual int add_type(int64_t n, int k) = 0;
+  virtual int add_relation(int ti, int tj, const void* data, int64_t ld, int src, int mem, int storage, int borrow,
+                           const uint8_t* mask, int64_t mask_ld, int mask_mem) = 0;
+  virtual void set_factor(int t, const void* G0, int64_t ld, int src, int mem) = 0;
+  virtual void set_backbone(int rel, const void* S, int64_t ld, int src, int mem) = 0;
+  virtual void set_split_terms(int terms) = 0;
+  virtual void finalize() = 0;
+  virtual void iterate(int algo, int n_iters, cudaStream_t st) = 0;
+  virtual void phase_products(int algo, cudaStream_t st) = 0;
+  virtual void phase_update(int algo, cudaStream_t st) = 0;
+  virtual void comm_small(void** ptr, int64_t* count) = 0;
+  virtual void comm_bpartial(int rel, void** full, void** local, int64_t* local_count, int* dtype) = 0;
+  virtual void comm_factor(int t, void** full, int64_t* local_count, int* dtype) = 0;
+  virtual void transform_prepare(int target, cudaStream_t st) = 0;
+  virtual void transform_iterate(int n_iters, cudaStream_t st) = 0;
+  virtual void get_factor(int t, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) = 0;
+  virtual void get_backbone(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) = 0;
+  virtual void objective(double* per_rel, double* total, cudaStream_t st) = 0;
+  virtual void complete(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// dtype-generic copy-in / copy-out helpers
+// ------------------------------------------------------------------------------------------------
+template <class ST, class DT>
+static void launch_convert(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, cudaStream_t st) {
+  if (rows * cols == 0) return;
+  convert_2d<ST, DT><<<nblk(rows * cols, 256), 256, 0, st>>>((const ST*)src, lds, (DT*)dst, ldd, rows, cols);
+}
+// device src (dtype sd) -> device dst (dtype dd)
+static void device_convert(const void* src, int64_t lds, int sd, void* dst, int64_t ldd, int dd, int64_t rows, int64_t cols,
+                           cudaStream_t st) {
+  if (rows * cols == 0) return;
+  const unsigned g = nblk(rows * cols, 256);
+  if (sd == FZ_BF16 && dd == FZ_BF16) {
+    CUDA_OK(cudaMemcpy2DAsync(dst, ldd * 2, src, lds * 2, cols * 2, rows, cudaMemcpyDeviceToDevice, st));
+  } else if (dd == FZ_BF16) {
+    if (sd == FZ_F64) convert_2d_to_bf16<double><<<g, 256, 0, st>>>((const double*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols);
+    else if (sd == FZ_F32) convert_2d_to_bf16<float><<<g, 256, 0, st>>>((const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols);
+    else FZ_THROW(FZ_ERR_INVALID, "unsupported conversion %d -> bf16", sd);
+  } else if (sd == FZ_BF16) {
+    if (dd == FZ_F64) convert_2d_from_bf16<double><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, lds, (double*)dst, ldd, rows, cols);
+    else if (dd == FZ_F32) convert_2d_from_bf16<float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, cols);
+    else FZ_THROW(FZ_ERR_INVALID, "unsupported conversion bf16 -> %d", dd);
+  } else if (sd == FZ_F64 && dd == FZ_F64) launch_convert<double, double>(src, lds, dst, ldd, rows, cols, st);
+  else if (sd == FZ_F64 && dd == FZ_F32) launch_convert<double, float>(src, lds, dst, ldd, rows, cols, st);
+  else if (sd == FZ_F32 && dd == FZ_F64) launch_convert<float, double>(src, lds, dst, ldd, rows, cols, st);
+  else if (sd == FZ_F32 && dd == FZ_F32) launch_convert<float, float>(src, lds, dst, ldd, rows, cols, st);
+  else if (sd == FZ_U8 && dd == FZ_U8) launch_convert<uint8_t, uint8_t>(src, lds, dst, ldd, rows, cols, st);
+  else FZ_THROW(FZ_ERR_INVALID, "unsupported conversion %d -> %d", sd, dd);
+  CUDA_OK(cudaGetLastError());
+}
+// caller buffer (host or device) -> engine device buffer, converting dtype
+static void copy_in(const void* src, int64_t lds, int sd, int mem, void* dst, int64_t ldd, int dd, int64_t rows, int64_t cols,
+                    cudaStream_t st) {
+  if (rows * cols == 0) return;
+  if (mem == FZ_DEVICE) {
+    device_convert(src, lds, sd, dst, ldd, dd, rows, cols, st);
+    return;
+  }
+  const size_t es = dtype_size(sd);
+  if (sd == dd) {
+    CUDA_OK(cudaMemcpy2DAsync(dst, ldd * es, src, lds * es, cols * es, rows, cudaMemcpyHostToDevice, st));
+    return;
+  }
+  DevBuf stage;
+  stage.alloc((size_t)rows * cols * es, false);
+  CUDA_OK(cudaMemcpy2DAsync(stage.p, cols * es, src, lds * es, cols * es, rows, cudaMemcpyHostToDevice, st));
+  device_convert(stage.p, cols, sd, dst, ldd, dd, rows, cols, st);
+  CUDA_OK(cudaStreamSynchronize(st));  // staging buffer dies here
+}
+// engine device buffer -> caller buffer (host or device)
+static void copy_out(const void* src, int64_t lds, int sd, void* dst, int64_t ldd, int dd, int mem, int64_t rows, int64_t cols,
+                     cudaStream_t st) {
+  if (rows * cols == 0) return;
+  if (mem == FZ_DEVICE) {
+    device_convert(src, lds, sd, dst, ldd, dd, rows, cols, st);
+    return;
+  }
+  const size_t es = dtype_size(dd);
+  if (sd == dd) {
+    CUDA_OK(cudaMemcpy2DAsync(dst, ldd * es, src, lds * es, cols * es, rows, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return;
+  }
+  DevBuf stage;
+  stage.alloc((size_t)rows * cols * es, false);
+  device_convert(src, lds, sd, stage.p, cols, dd, rows, cols, st);
+  CUDA_OK(cudaMemcpy2DAsync(dst, ldd * es, stage.p, cols * es, cols * es, rows, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+}
+
+template <class T> struct DtypeOf;
+template <> struct DtypeOf<float> { static constexpr int value = FZ_F32; };
+template <> struct DtypeOf<double> { static constexpr int value = FZ_F64; };
+
+// ------------------------------------------------------------------------------------------------
+template <class T>
+class Engine : public EngineBase {
+  static constexpr int kDT = DtypeOf<T>::value;
+  static constexpr int kKp = 64;  // padded width of one bf16 split term on the tensor-core path
+
+  struct TypeRec {
+    int64_t n = 0, n_pad = 0, m_loc = 0, row0 = 0, rows_loc = 0;
+    int k = 0;
+    DevBuf G[2];
+    int cur = 0;
+    bool has_factor = false;
+    bool need_gs = false;
+    DevBuf Gs;               // bf16 [n_pad][terms*kKp]
+    CUtensorMap tmG;
+    DevBuf gram_part;
+    int gram_chunks = 0, gram_rows_per_chunk = 0;
+    double* gram_raw = nullptr;  // inside `small`
+    DevBuf gram, P, pinv_work, info;
+    DevBuf Nsum, Dsum;           // T k*k
+    DevBuf thP, thN;             // T [m_loc][k]
+    std::vector<int> thetas, row_rels, col_rels;
+    DevBuf upd_terms, upd_adds, sum_ptrs;
+    int n_terms = 0, n_adds = 0;
+  };
+  struct RelRec {
+    int ti = 0, tj = 0, storage = FZ_F32;
+    bool theta = false, borrowed = false;
+    void* data = nullptr;
+    int64_t ld = 0, rows_loc = 0, cols = 0;
+    DevBuf own;
+    uint8_t* mask = nullptr;
+    int64_t mask_ld = 0;
+    DevBuf mask_own;
+    DevBuf A, B, Bloc, T1, E, Es, Cx;
+    double* M_raw = nullptr;
+    DevBuf M_part;
+    int m_chunks = 0, m_rows_per_chunk = 0;
+    DevBuf S, t2, t5, W1, W4, work;
+    bool has_backbone = false;
+    CUtensorMap tmX, tmXT, tmEs;
+  };
+
+  int device_;
+  int world_ = 1, rank_ = 0;
+  int terms_ = 2;
+  bool finalized_ = false;
+  bool dfmc_started_ = false;
+  std::vector<std::unique_ptr<TypeRec>> types_;
+  std::vector<std::unique_ptr<RelRec>> rels_;
+  DevBuf small_;
+  int64_t small_count_ = 0;
+  DevBuf pinv_jobs_, bb_jobs_, sum_jobs_;
+  DevBuf err_acc_;
+  // transform state
+  int tf_target_ = -1;
+  DevBuf tf_Cp_, tf_Cn_;
+  std::vector<int> tf_sum_types_;
+
+ public:
+  explicit Engine(int device) : device_(device) {}
+  int compute_dtype() const override { return kDT; }
+
+  void set_shard(int world, int rank) override {
+    if (!types_.empty()) FZ_THROW(FZ_ERR_INVALID, "fz_set_shard must precede fz_add_type");
+    if (world < 1 || rank < 0 || rank >= world) FZ_THROW(FZ_ERR_INVALID, "bad shard %d/%d", rank, world);
+    world_ = world;
+    rank_ = rank;
+  }
+
+  int add_type(int64_t n, int k) override {
+    if (finalized_) FZ_THROW(FZ_ERR_INVALID, "engine already finalized");
+    if (n <= 0 || k <= 0) FZ_THROW(FZ_ERR_INVALID, "object type needs n > 0 and rank > 0 (got %lld, %d)", (long long)n, k);
+    auto t = std::make_unique<TypeRec>();
+    t->n = n;
+    t->k = k;
+    t->m_loc = (n + world_ - 1) / world_;
+    t->n_pad = t->m_loc * world_;
+    t->row0 = (int64_t)rank_ * t->m_loc;
+    t->rows_loc = std::max<int64_t>(0, std::min<int64_t>(n, t->row0 + t->m_loc) - t->row0);
+    t->G[0].alloc((size_t)t->n_pad * k * sizeof(T));
+    t->G[1].alloc((size_t)t->n_pad * k * sizeof(T));
+    types_.push_back(std::move(t));
+    return (int)types_.size() - 1;
+  }
+
+  int add_relation(int ti, int tj, const void* data, int64_t ld, int src, int mem, int storage, int borrow,
+                   const uint8_t* mask, int64_t mask_ld, int mask_mem) override {
+    if (finalized_) FZ_THROW(FZ_ERR_INVALID, "engine already finalized");
+    if (ti < 0 || tj < 0 || ti >= (int)types_.size() || tj >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id");
+    if (data == nullptr) FZ_THROW(FZ_ERR_INVALID, "relation data is NULL");
+    auto r = std::make_unique<RelRec>();
+    r->ti = ti;
+    r->tj = tj;
+    r->theta = (ti == tj);
+    TypeRec& Ti = *types_[ti];
+    TypeRec& Tj = *types_[tj];
+    r->rows_loc = Ti.rows_loc;
+    r->cols = Tj.n;
+    if (storage != FZ_BF16) storage = kDT;  // CUDA-core path keeps the relation in the compute dtype
+    if (storage == FZ_BF16 && (r->theta || mask != nullptr)) storage = kDT;  // constraints / completion stay exact
+    if (storage == FZ_BF16 && kDT != FZ_F32) FZ_THROW(FZ_ERR_UNSUPPORTED, "bf16 relations need the fp32 engine");
+    if (storage == FZ_BF16 && (Ti.k > kKp || Tj.k > kKp))
+      FZ_THROW(FZ_ERR_UNSUPPORTED, "tensor-core path supports rank <= %d (got %d, %d)", kKp, Ti.k, Tj.k);
+    r->storage = storage;
+    cudaStream_t st = 0;
+    if (borrow) {
+      if (mem != FZ_DEVICE || src != storage) FZ_THROW(FZ_ERR_INVALID, "borrowed relations must be device memory in the storage dtype");
+      if (mask != nullptr) FZ_THROW(FZ_ERR_INVALID, "masked relations are rewritten by dfmc and cannot be borrowed");
+      if (storage == FZ_BF16 && ((ld % 8) != 0 || ((uintptr_t)data & 15) != 0))
+        FZ_THROW(FZ_ERR_INVALID, "borrowed bf16 relation needs 16-byte alignment and ld %% 8 == 0");
+      r->data = const_cast<void*>(data);
+      r->ld = ld;
+      r->borrowed = true;
+    } else {
+      const int64_t ldo = (storage == FZ_BF16) ? ((r->cols + 7) / 8) * 8 : r->cols;
+      r->own.alloc((size_t)std::max<int64_t>(1, r->rows_loc) * ldo * dtype_size(storage));
+      copy_in(data, ld, src, mem, r->own.p, ldo, storage, r->rows_loc, r->cols, st);
+      r->data = r->own.p;
+      r->ld = ldo;
+    }
+    if (mask != nullptr) {
+      if (r->theta) FZ_THROW(FZ_ERR_INVALID, "constraint matrices cannot be masked");
+      r->mask_own.alloc((size_t)std::max<int64_t>(1, r->rows_loc) * r->cols);
+      copy_in(mask, mask_ld, FZ_U8, mask_mem, r->mask_own.p, r->cols, FZ_U8, r->rows_loc, r->cols, st);
+      r->mask = r->mask_own.template as<uint8_t>();
+      r->mask_ld = r->cols;
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+    const int id = (int)rels_.size();
+    if (r->theta) Ti.thetas.push_back(id);
+    else {
+      Ti.row_rels.push_back(id);
+      Tj.col_rels.push_back(id);
+      if (storage == FZ_BF16) { Ti.need_gs = true; Tj.need_gs = true; }
+    }
+    rels_.push_back(std::move(r));
+    return id;
+  }
+
+  void set_factor(int t, const void* G0, int64_t ld, int src, int mem) override {
+    if (t < 0 || t >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id %d", t);
+    TypeRec& Tt = *types_[t];
+    copy_in(G0, ld, src, mem, Tt.G[Tt.cur].p, Tt.k, kDT, Tt.n, Tt.k, 0);
+    CUDA_OK(cudaStreamSynchronize(0));
+    Tt.has_factor = true;
+  }
+
+  void set_backbone(int rel, const void* S, int64_t ld, int src, int mem) override {
+    if (!finalized_) FZ_THROW(FZ_ERR_INVALID, "fz_set_backbone needs a finalized engine");
+    RelRec& r = relation(rel);
+    if (r.theta) FZ_THROW(FZ_ERR_INVALID, "constraint matrices have no backbone");
+    copy_in(S, ld, src, mem, r.S.p, types_[r.tj]->k, FZ_F64, types_[r.ti]->k, types_[r.tj]->k, 0);
+    CUDA_OK(cudaStreamSynchronize(0));
+    r.has_backbone = true;
+  }
+
+  void set_split_terms(int terms) override {
+    if (finalized_) FZ_THROW(FZ_ERR_INVALID, "engine already finalized");
+    if (terms < 1 || terms > 3) FZ_THROW(FZ_ERR_INVALID, "split terms must be 1..3");
+    terms_ = terms;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  void finalize() override {
+    if (finalized_) return;
+    if (types_.empty()) FZ_THROW(FZ_ERR_INVALID, "no object types");
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device_));
+    const int sms = prop.multiProcessorCount;
+    // fp64 all-reduce buffer: [gram_t ...][M_r ...]
+    small_count_ = 0;
+    for (auto& t : types_) small_count_ += (int64_t)t->k * t->k;
+    for (auto& r : rels_)
+      if (!r->theta) small_count_ += (int64_t)types_[r->ti]->k * types_[r->tj]->k;
+    small_.alloc((size_t)small_count_ * 8);
+    int64_t off = 0;
+    for (auto& tp : types_) {
+      TypeRec& t = *tp;
+      t.gram_raw = small_.template as<double>() + off;
+      off += (int64_t)t.k * t.k;
+      t.gram_rows_per_chunk = (int)std::max<int64_t>(64, (t.m_loc + 2 * sms - 1) / (2 * sms));
+      t.gram_rows_per_chunk = ((t.gram_rows_per_chunk + 15) / 16) * 16;
+      t.gram_chunks = (int)std::max<int64_t>(1, (t.m_loc + t.gram_rows_per_chunk - 1) / t.gram_rows_per_chunk);
+      t.gram_part.alloc((size_t)t.gram_chunks * t.k * t.k * 8);
+      t.gram.alloc((size_t)t.k * t.k * 8);
+      t.P.alloc((size_t)t.k * t.k * 8);
+      t.pinv_work.alloc((size_t)3 * t.k * t.k * 8);
+      t.info.alloc(2 * sizeof(int));
+      t.Nsum.alloc((size_t)t.k * t.k * sizeof(T));
+      t.Dsum.alloc((size_t)t.k * t.k * sizeof(T));
+      if (!t.thetas.empty()) {
+        t.thP.alloc((size_t)t.m_loc * t.k * sizeof(T));
+        t.thN.alloc((size_t)t.m_loc * t.k * sizeof(T));
+      }
+      if (t.need_gs) {
+        t.Gs.alloc((size_t)t.n_pad * terms_ * kKp * 2);
+        std::string e;
+        if (!make_tmap_bf16_2d(&t.tmG, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 64, &e))
+          FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+      }
+    }
+    for (auto& rp : rels_) {
+      RelRec& r = *rp;
+      if (r.theta) continue;
+      TypeRec& Ti = *types_[r.ti];
+      TypeRec& Tj = *types_[r.tj];
+      r.M_raw = small_.template as<double>() + off;
+      off += (int64_t)Ti.k * Tj.k;
+      r.A.alloc((size_t)std::max<int64_t>(1, Ti.m_loc) * Tj.k * sizeof(T));
+      r.B.alloc((size_t)Tj.n_pad * Ti.k * sizeof(T));
+      if (world_ > 1) r.Bloc.alloc((size_t)Tj.m_loc * Ti.k * sizeof(T));
+      r.m_rows_per_chunk = Ti.gram_rows_per_chunk;
+      r.m_chunks = Ti.gram_chunks;
+      r.M_part.alloc((size_t)r.m_chunks * Ti.k * Tj.k * 8);
+      r.S.alloc((size_t)Ti.k * Tj.k * 8);
+      r.t2.alloc((size_t)Ti.k * Ti.k * 8);
+      r.t5.alloc((size_t)Tj.k * Tj.k * 8);
+      r.W1.alloc((size_t)Ti.k * Tj.k * sizeof(T));
+      r.W4.alloc((size_t)Ti.k * Tj.k * sizeof(T));
+      const int km = std::max(Ti.k, Tj.k);
+      r.work.alloc((size_t)2 * km * km * 8);
+      if (r.storage == FZ_BF16) {
+        std::string e;
+        bool ok = make_tmap_bf16_2d(&r.tmX, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols, (uint64_t)r.ld, 64, 128, &e) &&
+                  make_tmap_bf16_2d(&r.tmXT, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols, (uint64_t)r.ld, 64, 64, &e);
+        if (!ok) FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+      }
+    }
+    err_acc_.alloc(8);
+    build_job_tables();
+    // opt in to the large dynamic shared memory of the tensor-core kernels
+    set_umma_attrs();
+    CUDA_OK(cudaDeviceSynchronize());
+    finalized_ = true;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  void iterate(int algo, int n_iters, cudaStream_t st) override {
+    need_final();
+    if (world_ != 1) FZ_THROW(FZ_ERR_INVALID, "fz_iterate is for unsharded handles; use the fz_phase_* calls");
+    for (int it = 0; it < n_iters; ++it) {
+      phase_products(algo, st);
+      phase_update(algo, st);
+    }
+  }
+
+  void phase_products(int algo, cudaStream_t st) override {
+    need_final();
+    check_factors();
+    if (algo == FZ_DFMC) {
+      if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "dfmc is single-GPU in this round");
+      if (!dfmc_started_) {
+        for (auto& rp : rels_)                                   // _dfmc.py:287-292
+          if (rp->mask) {
+            mask_zero<T><<<nblk(rp->rows_loc * rp->cols, 256), 256, 0, st>>>((T*)rp->data, rp->ld, rp->mask, rp->mask_ld,
+                                                                              rp->rows_loc, rp->cols);
+            ++launches;
+          }
+        dfmc_started_ = true;
+      }
+      grams(st);
+      for (auto& rp : rels_)
+        if (!rp->theta) { product_A(*rp, st); reduce_M(*rp, st); }
+      return;  // the second half (imputation, A/B on the completed R) runs in phase_update
+    }
+    grams(st);
+    for (auto& rp : rels_) {
+      if (rp->theta) continue;
+      product_A(*rp, st);
+      product_B(*rp, st);
+      reduce_M(*rp, st);
+    }
+    theta_products(st);
+    CUDA_OK(cudaGetLastError());
+  }
+
+  void phase_update(int algo, cudaStream_t st) override {
+    need_final();
+    const bool dfmf = (algo == FZ_DFMF);
+    run_chain(/*solve=*/true, /*scrub=*/dfmf, st);
+    if (!dfmf) {
+      for (auto& rp : rels_) {                                   // _dfmc.py:319-325
+        RelRec& r = *rp;
+        if (r.theta || !r.mask) continue;
+        TypeRec& Ti = *types_[r.ti];
+        TypeRec& Tj = *types_[r.tj];
+        ensure_T1(r);
+        gemm(cur(Ti), Ti.k, r.W4.template as<T>(), Tj.k, r.T1.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, Ti.k, false, st);
+        dim3 g(nblk(r.cols, 32), nblk(r.rows_loc, 32));
+        impute_masked<T><<<g, 256, 0, st>>>((T*)r.data, r.ld, r.mask, r.mask_ld, r.T1.template as<T>(), Tj.k, cur(Tj), Tj.k,
+                                            r.rows_loc, r.cols, Tj.k);
+        ++launches;
+      }
+      for (auto& rp : rels_) {
+        if (rp->theta) continue;
+        if (rp->mask) product_A(*rp, st);   // only completed relations changed
+        product_B(*rp, st);
+      }
+      theta_products(st);
+    }
+    for (size_t t = 0; t < types_.size(); ++t) update_type((int)t, dfmf ? 1 : 0, st);
+    for (auto& tp : types_) tp->cur ^= 1;
+    CUDA_OK(cudaGetLastError());
+  }
+
+  void comm_small(void** ptr, int64_t* count) override {
+    need_final();
+    *ptr = small_.p;
+    *count = small_count_;
+  }
+  void comm_bpartial(int rel, void** full, void** local, int64_t* local_count, int* dtype) override {
+    need_final();
+    RelRec& r = relation(rel);
+    if (r.theta) FZ_THROW(FZ_ERR_INVALID, "constraint matrices have no B partial");
+    *full = r.B.p;
+    *local = (world_ > 1) ? r.Bloc.p : r.B.p;
+    *local_count = types_[r.tj]->m_loc * types_[r.ti]->k;
+    *dtype = kDT;
+  }
+  void comm_factor(int t, void** full, int64_t* local_count, int* dtype) override {
+    need_final();
+    if (t < 0 || t >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id %d", t);
+    TypeRec& Tt = *types_[t];
+    *full = Tt.G[Tt.cur].p;
+    *local_count = Tt.m_loc * Tt.k;
+    *dtype = kDT;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // transform (_dfmf.py:330-458): frozen G_j / S, loop-invariant relation terms computed once.
+  void transform_prepare(int target, cudaStream_t st) override {
+    need_final();
+    check_factors();
+    if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "transform runs on replicas (rows are independent), not shards");
+    if (target < 0 || target >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown target type");
+    TypeRec& Tt = *types_[target];
+    tf_target_ = target;
+    tf_Cp_.alloc((size_t)Tt.n * Tt.k * sizeof(T));
+    tf_Cn_.alloc((size_t)Tt.n * Tt.k * sizeof(T));
+    for (auto& rp : rels_) {
+      if (rp->theta) { if (rp->ti != target) FZ_THROW(FZ_ERR_INVALID, "constraint on a non-target type in transform"); continue; }
+      if (rp->ti != target && rp->tj != target) FZ_THROW(FZ_ERR_INVALID, "relation must include the target object type");
+      if (!rp->has_backbone) FZ_THROW(FZ_ERR_INVALID, "relation without a backbone (fz_set_backbone)");
+    }
+    grams(st);
+    run_chain(/*solve=*/false, /*scrub=*/false, st);   // t2 / t5 / W1 / W4 from the given S
+    for (auto& rp : rels_) {
+      RelRec& r = *rp;
+      if (r.theta) continue;
+      TypeRec& Ti = *types_[r.ti];
+      TypeRec& Tj = *types_[r.tj];
+      const bool row_role = (r.ti == target);
+      TypeRec& To = row_role ? Tj : Ti;   // the frozen other type
+      // E = G_other * (S^T or S)   (n_other x k_t)      _dfmf.py:394 / :408
+      r.E.alloc((size_t)To.n * Tt.k * sizeof(T));
+      const T* W = row_role ? r.W1.template as<T>() : r.W4.template as<T>();
+      gemm(cur(To), To.k, W, Tt.k, r.E.template as<T>(), Tt.k, (int)To.n, Tt.k, To.k, false, st);
+      r.Cx.alloc((size_t)Tt.n * Tt.k * sizeof(T));
+      if (r.storage == FZ_BF16) {
+        r.Es.alloc((size_t)To.n * terms_ * kKp * 2);
+        split_factor<T><<<nblk(To.n * kKp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(),
+                                                                To.n, To.n, Tt.k, kKp, terms_);
+        ++launches;
+        std::string e;
+        if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 64, &e))
+          FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+        umma(r, /*trans=*/!row_role, r.tmEs, 0, r.Cx.template as<T>(), Tt.k, (int)Tt.n, (int)To.n, Tt.k, st);
+      } else {
+        if (row_role) gemm((const T*)r.data, r.ld, r.E.template as<T>(), Tt.k, r.Cx.template as<T>(), Tt.k, (int)Tt.n, Tt.k, (int)To.n, false, st);
+        else gemm_t((const T*)r.data, r.ld, r.E.template as<T>(), Tt.k, r.Cx.template as<T>(), Tt.k, (int)Tt.n, Tt.k, (int)To.n, st);
+      }
+      accum_sign_split<T><<<nblk(Tt.n * Tt.k, 256), 256, 0, st>>>(r.Cx.template as<T>(), tf_Cp_.template as<T>(),
+                                                                   tf_Cn_.template as<T>(), Tt.n * Tt.k);
+      ++launches;
+    }
+    CUDA_OK(cudaGetLastError());
+  }
+
+  void transform_iterate(int n_iters, cudaStream_t st) override {
+    need_final();
+    if (tf_target_ < 0) FZ_THROW(FZ_ERR_INVALID, "fz_transform_prepare first");
+    TypeRec& Tt = *types_[tf_target_];
+    for (int it = 0; it < n_iters; ++it) {
+      theta_products(st);
+      update_type(tf_target_, 0, st);
+      Tt.cur ^= 1;
+    }
+    CUDA_OK(cudaGetLastError());
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  void get_factor(int t, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) override {
+    need_final();
+    if (t < 0 || t >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id %d", t);
+    TypeRec& Tt = *types_[t];
+    copy_out(Tt.G[Tt.cur].p, Tt.k, kDT, dst, ld, dd, mem, Tt.n, Tt.k, st);
+  }
+  void get_backbone(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) override {
+    need_final();
+    RelRec& r = relation(rel);
+    if (r.theta) FZ_THROW(FZ_ERR_INVALID, "constraint matrices have no backbone");
+    copy_out(r.S.p, types_[r.tj]->k, FZ_F64, dst, ld, dd, mem, types_[r.ti]->k, types_[r.tj]->k, st);
+  }
+
+  void objective(double* per_rel, double* total, cudaStream_t st) override {
+    need_final();
+    if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "objective on sharded handles is not implemented");
+    double sum = 0.0;
+    int idx = 0;
+    for (auto& rp : rels_) {
+      RelRec& r = *rp;
+      if (r.theta) continue;
+      TypeRec& Ti = *types_[r.ti];
+      TypeRec& Tj = *types_[r.tj];
+      ensure_T1(r);
+      gemm(cur(Ti), Ti.k, r.W4.template as<T>(), Tj.k, r.T1.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, Ti.k, false, st);
+      CUDA_OK(cudaMemsetAsync(err_acc_.p, 0, 8, st));
+      dim3 g(nblk(r.cols, 32), nblk(r.rows_loc, 32));
+      if (r.storage == FZ_BF16)
+        recon_err<T, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.T1.template as<T>(), Tj.k, cur(Tj),
+                                                       Tj.k, r.rows_loc, r.cols, Tj.k, err_acc_.template as<double>(), nullptr, 0);
+      else
+        recon_err<T, T><<<g, 256, 0, st>>>((const T*)r.data, r.ld, r.T1.template as<T>(), Tj.k, cur(Tj), Tj.k, r.rows_loc, r.cols,
+                                           Tj.k, err_acc_.template as<double>(), nullptr, 0);
+      ++launches;
+      double sq = 0.0;
+      CUDA_OK(cudaMemcpyAsync(&sq, err_acc_.p, 8, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      const double e = std::sqrt(sq);
+      if (per_rel) per_rel[idx] = e;
+      ++idx;
+      sum += e;
+    }
+    if (total) *total = sum;
+  }
+
+  void complete(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) override {
+    need_final();
+    RelRec& r = relation(rel);
+    if (r.theta) FZ_THROW(FZ_ERR_INVALID, "constraint matrices cannot be completed");
+    TypeRec& Ti = *types_[r.ti];
+    TypeRec& Tj = *types_[r.tj];
+    ensure_T1(r);
+    gemm(cur(Ti), Ti.k, r.W4.template as<T>(), Tj.k, r.T1.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, Ti.k, false, st);
+    DevBuf out;
+    out.alloc((size_t)std::max<int64_t>(1, r.rows_loc) * r.cols * sizeof(T), false);
+    dim3 g(nblk(r.cols, 32), nblk(r.rows_loc, 32));
+    recon_err<T, T><<<g, 256, 0, st>>>(nullptr, 0, r.T1.template as<T>(), Tj.k, cur(Tj), Tj.k, r.rows_loc, r.cols, Tj.k, nullptr,
+                                       out.template as<T>(), r.cols);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    copy_out(out.p, r.cols, kDT, dst, ld, dd, mem, r.rows_loc, r.cols, st);
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+
+ private:
+  // ---------------------------------------------------------------------------------------------
+  void need_final() const {
+    if (!finalized_) FZ_THROW(FZ_ERR_INVALID, "call fz_finalize first");
+  }
+  void check_factors() const {
+    for (auto& t : types_)
+      if (!t->has_factor) FZ_THROW(FZ_ERR_INVALID, "a factor was never set (fz_set_factor)");
+  }
+  RelRec& relation(int rel) {
+    if (rel < 0 || rel >= (int)rels_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown relation id %d", rel);
+    return *rels_[rel];
+  }
+  T* cur(TypeRec& t) { return t.G[t.cur].template as<T>(); }
+  T* nxt(TypeRec& t) { return t.G[t.cur ^ 1].template as<T>(); }
+  void ensure_T1(RelRec& r) {
+    if (!r.T1.p) r.T1.alloc((size_t)std::max<int64_t>(1, r.rows_loc) * types_[r.tj]->k * sizeof(T), false);
+  }
+
+  // C = X * Y (CUDA cores, exact in T)
+  void gemm(const T* X, int64_t ldx, const T* Y, int64_t ldy, T* C, int64_t ldc, int M, int N, int K, bool accumulate,
+            cudaStream_t st) {
+    if (M <= 0 || N <= 0) return;
+    dim3 g(nblk(M, kGemmBM), nblk(N, kGemmBN));
+    gemm_simt<T, T, false, false><<<g, 256, 0, st>>>(X, ldx, Y, ldy, C, nullptr, ldc, M, N, K, accumulate ? 1 : 0);
+    ++launches;
+  }
+  // C = X^T * Y, X is K x M
+  void gemm_t(const T* X, int64_t ldx, const T* Y, int64_t ldy, T* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return;
+    dim3 g(nblk(M, kGemmBM), nblk(N, kGemmBN));
+    gemm_simt<T, T, true, false><<<g, 256, 0, st>>>(X, ldx, Y, ldy, C, nullptr, ldc, M, N, K, 0);
+    ++launches;
+  }
+
+  template <int N, bool TR>
+  void umma_launch(const CUtensorMap& tx, const CUtensorMap& tg, const SkinnyParams& p, int ksplit, cudaStream_t st) {
+    using Cfg = SkinnyCfg<N>;
+    dim3 grid((p.M + kSkBM - 1) / kSkBM, ksplit);
+    umma_skinny_kernel<N, TR><<<grid, kSkThreads, Cfg::kSmemBytes, st>>>(tx, tg, p);
+    ++launches;
+  }
+  template <int N, bool TR>
+  static void umma_attr() {
+    cudaFuncSetAttribute(umma_skinny_kernel<N, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkinnyCfg<N>::kSmemBytes);
+  }
+  void set_umma_attrs() {
+    umma_attr<64, false>(); umma_attr<64, true>();
+    umma_attr<128, false>(); umma_attr<128, true>();
+    umma_attr<192, false>(); umma_attr<192, true>();
+  }
+  // tensor-core product of a bf16 relation with a split factor:  C (M x k) = op(R) * Gs[g_row0 + ., :]
+  void umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g_row0, T* C, int64_t ldc, int M, int K, int k, cudaStream_t st);
+
+  void split(TypeRec& t, cudaStream_t st) {
+    split_factor<T><<<nblk(t.n_pad * kKp, 256), 256, 0, st>>>(cur(t), t.k, t.Gs.template as<__nv_bfloat16>(), t.n, t.n_pad, t.k, kKp,
+                                                               terms_);
+    ++launches;
+  }
+
+  // Gram matrices of the current factors over the local rows (+ bf16 operand form where needed)
+  void grams(cudaStream_t st) {
+    for (auto& tp : types_) {
+      TypeRec& t = *tp;
+      if (t.need_gs) split(t, st);
+      const T* Gl = cur(t) + t.row0 * t.k;
+      dim3 g(t.gram_chunks, nblk(t.k, 64), nblk(t.k, 64));
+      gram_partial<T><<<g, 256, 0, st>>>(Gl, t.k, Gl, t.k, t.gram_part.template as<double>(), t.rows_loc, t.k, t.k,
+                                         t.gram_rows_per_chunk, 0);
+      reduce_partials<<<nblk((long long)t.k * t.k, 256), 256, 0, st>>>(t.gram_part.template as<double>(), t.gram_raw, t.gram_chunks,
+                                                                       (long long)t.k * t.k);
+      launches += 2;
+    }
+  }
+
+  void product_A(RelRec& r, cudaStream_t st) {   // A = R G_j   (local rows of type i)
+    TypeRec& Tj = *types_[r.tj];
+    if (r.rows_loc <= 0) return;
+    if (r.storage == FZ_BF16) umma(r, false, Tj.tmG, 0, r.A.template as<T>(), Tj.k, (int)r.rows_loc, (int)r.cols, Tj.k, st);
+    else gemm((const T*)r.data, r.ld, cur(Tj), Tj.k, r.A.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, (int)r.cols, false, st);
+  }
+  void product_B(RelRec& r, cudaStream_t st) {   // B = R^T G_i[local rows]   (all rows of type j)
+    TypeRec& Ti = *types_[r.ti];
+    TypeRec& Tj = *types_[r.tj];
+    if (r.rows_loc <= 0) {
+      CUDA_OK(cudaMemsetAsync(r.B.p, 0, r.B.bytes, st));
+      return;
+    }
+    if (r.storage == FZ_BF16) umma(r, true, Ti.tmG, Ti.row0, r.B.template as<T>(), Ti.k, (int)r.cols, (int)r.rows_loc, Ti.k, st);
+    else gemm_t((const T*)r.data, r.ld, cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.B.template as<T>(), Ti.k, (int)r.cols, Ti.k, (int)r.rows_loc, st);
+  }
+  void reduce_M(RelRec& r, cudaStream_t st) {    // M = G_i[local]^T A    (fp64 accumulate)
+    TypeRec& Ti = *types_[r.ti];
+    TypeRec& Tj = *types_[r.tj];
+    dim3 g(r.m_chunks, nblk(Ti.k, 64), nblk(Tj.k, 64));
+    gram_partial<T><<<g, 256, 0, st>>>(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.A.template as<T>(), Tj.k, r.M_part.template as<double>(),
+                                       r.rows_loc, Ti.k, Tj.k, r.m_rows_per_chunk, 0);
+    reduce_partials<<<nblk((long long)Ti.k * Tj.k, 256), 256, 0, st>>>(r.M_part.template as<double>(), r.M_raw, r.m_chunks,
+                                                                       (long long)Ti.k * Tj.k);
+    launches += 2;
+  }
+  void theta_products(cudaStream_t st) {         // Theta+ G -> den, Theta- G -> num   (_dfmf.py:284-292)
+    for (auto& tp : types_) {
+      TypeRec& t = *tp;
+      bool first = true;
+      for (int id : t.thetas) {
+        RelRec& r = *rels_[id];
+        if (r.rows_loc <= 0) continue;
+        dim3 g(nblk(r.rows_loc, kGemmBM), nblk(t.k, kGemmBN));
+        gemm_simt<T, T, false, true><<<g, 256, 0, st>>>((const T*)r.data, r.ld, cur(t), t.k, t.thP.template as<T>(),
+                                                         t.thN.template as<T>(), t.k, (int)r.rows_loc, t.k, (int)r.cols, first ? 0 : 1);
+        ++launches;
+        first = false;
+      }
+    }
+  }
+
+  void build_job_tables() {
+    std::vector<PinvJob> pj;
+    for (auto& tp : types_) {
+      TypeRec& t = *tp;
+      PinvJob j;
+      j.gram_raw = t.gram_raw;
+      j.gram = t.gram.template as<double>();
+      j.P = t.P.template as<double>();
+      j.work = t.pinv_work.template as<double>();
+      j.info = t.info.template as<int>();
+      j.k = t.k;
+      pj.push_back(j);
+    }
+    pinv_jobs_.alloc(pj.size() * sizeof(PinvJob));
+    CUDA_OK(cudaMemcpy(pinv_jobs_.p, pj.data(), pj.size() * sizeof(PinvJob), cudaMemcpyHostToDevice));
+
+    std::vector<BackboneJob<T>> bj;
+    for (auto& rp : rels_) {
+      RelRec& r = *rp;
+      if (r.theta) continue;
+      TypeRec& Ti = *types_[r.ti];
+      TypeRec& Tj = *types_[r.tj];
+      BackboneJob<T> j;
+      j.M_raw = r.M_raw;
+      j.P_i = Ti.P.template as<double>();
+      j.P_j = Tj.P.template as<double>();
+      j.gram_i = Ti.gram.template as<double>();
+      j.gram_j = Tj.gram.template as<double>();
+      j.S = r.S.template as<double>();
+      j.t2 = r.t2.template as<double>();
+      j.t5 = r.t5.template as<double>();
+      j.W1 = r.W1.template as<T>();
+      j.W4 = r.W4.template as<T>();
+      j.work = r.work.template as<double>();
+      j.ki = Ti.k;
+      j.kj = Tj.k;
+      j.solve = 1;
+      j.scrub = 1;
+      bj.push_back(j);
+    }
+    bb_host_ = bj;
+    bb_jobs_.alloc(std::max<size_t>(1, bj.size()) * sizeof(BackboneJob<T>));
+
+    std::vector<TypeSumJob<T>> sj;
+    for (auto& tp : types_) {
+      TypeRec& t = *tp;
+      std::vector<const double*> ptrs;
+      for (int id : t.row_rels) ptrs.push_back(rels_[id]->t2.template as<double>());
+      for (int id : t.col_rels) ptrs.push_back(rels_[id]->t5.template as<double>());
+      t.sum_ptrs.alloc(std::max<size_t>(1, ptrs.size()) * sizeof(double*));
+      if (!ptrs.empty()) CUDA_OK(cudaMemcpy(t.sum_ptrs.p, ptrs.data(), ptrs.size() * sizeof(double*), cudaMemcpyHostToDevice));
+      TypeSumJob<T> j;
+      j.mats = t.sum_ptrs.template as<const double*>();
+      j.Nsum = t.Nsum.template as<T>();
+      j.Dsum = t.Dsum.template as<T>();
+      j.n_mats = (int)ptrs.size();
+      j.k = t.k;
+      sj.push_back(j);
+      // update terms (device tables; X pointers are fixed for the lifetime of the handle)
+      std::vector<UpdTerm<T>> terms;
+      for (int id : t.row_rels) {
+        RelRec& r = *rels_[id];
+        UpdTerm<T> u;
+        u.X = r.A.template as<T>();
+        u.ldx = types_[r.tj]->k;
+        u.W = r.W1.template as<T>();
+        u.kx = types_[r.tj]->k;
+        u.pad_ = 0;
+        terms.push_back(u);
+      }
+      for (int id : t.col_rels) {
+        RelRec& r = *rels_[id];
+        UpdTerm<T> u;
+        u.X = (world_ > 1) ? r.Bloc.template as<T>() : r.B.template as<T>();
+        u.ldx = types_[r.ti]->k;
+        u.W = r.W4.template as<T>();
+        u.kx = types_[r.ti]->k;
+        u.pad_ = 0;
+        terms.push_back(u);
+      }
+      t.n_terms = (int)terms.size();
+      t.upd_terms.alloc(std::max<size_t>(1, terms.size()) * sizeof(UpdTerm<T>));
+      if (!terms.empty()) CUDA_OK(cudaMemcpy(t.upd_terms.p, terms.data(), terms.size() * sizeof(UpdTerm<T>), cudaMemcpyHostToDevice));
+      std::vector<UpdAdd<T>> adds;
+      if (!t.thetas.empty()) {
+        UpdAdd<T> a;
+        a.num = t.thN.template as<T>();
+        a.den = t.thP.template as<T>();
+        adds.push_back(a);
+      }
+      t.n_adds = (int)adds.size();
+      t.upd_adds.alloc(2 * sizeof(UpdAdd<T>));
+      if (!adds.empty()) CUDA_OK(cudaMemcpy(t.upd_adds.p, adds.data(), adds.size() * sizeof(UpdAdd<T>), cudaMemcpyHostToDevice));
+    }
+    sum_jobs_.alloc(sj.size() * sizeof(TypeSumJob<T>));
+    CUDA_OK(cudaMemcpy(sum_jobs_.p, sj.data(), sj.size() * sizeof(TypeSumJob<T>), cudaMemcpyHostToDevice));
+    bb_mode_ = -1;
+  }
+
+  std::vector<BackboneJob<T>> bb_host_;
+  int bb_mode_ = -1;
+
+  void run_chain(bool solve, bool scrub_small, cudaStream_t st) {
+    const int mode = (solve ? 2 : 0) | (scrub_small ? 1 : 0);
+    if (mode != bb_mode_ && !bb_host_.empty()) {
+      for (auto& j : bb_host_) { j.solve = solve ? 1 : 0; j.scrub = scrub_small ? 1 : 0; }
+      CUDA_OK(cudaMemcpyAsync(bb_jobs_.p, bb_host_.data(), bb_host_.size() * sizeof(BackboneJob<T>), cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      bb_mode_ = mode;
+    }
+    pinv_spd<<<(unsigned)types_.size(), kChainThreads, 0, st>>>(pinv_jobs_.template as<PinvJob>());
+    ++launches;
+    if (!bb_host_.empty()) {
+      backbone_chain<T><<<(unsigned)bb_host_.size(), kChainThreads, 0, st>>>(bb_jobs_.template as<BackboneJob<T>>());
+      ++launches;
+    }
+    type_sums<T><<<(unsigned)types_.size(), 256, 0, st>>>(sum_jobs_.template as<TypeSumJob<T>>());
+    ++launches;
+  }
+
+  void update_type(int t, int scrub_terms, cudaStream_t st) {
+    TypeRec& Tt = *types_[t];
+    if (Tt.rows_loc <= 0) return;
+    UpdArgs<T> a;
+    a.G = cur(Tt) + Tt.row0 * Tt.k;
+    a.Gnew = nxt(Tt) + Tt.row0 * Tt.k;
+    a.ldg = Tt.k;
+    a.rows = Tt.rows_loc;
+    a.kt = Tt.k;
+    a.scrub_terms = scrub_terms;
+    a.Nsum = Tt.Nsum.template as<T>();
+    a.Dsum = Tt.Dsum.template as<T>();
+    if (tf_target_ >= 0) {
+      // transform: no live relation terms; frozen sums + constraints enter additively
+      std::vector<UpdAdd<T>> adds;
+      UpdAdd<T> c;
+      c.num = tf_Cp_.template as<T>();
+      c.den = tf_Cn_.template as<T>();
+      adds.push_back(c);
+      if (!Tt.thetas.empty()) {
+        UpdAdd<T> th;
+        th.num = Tt.thN.template as<T>();
+        th.den = Tt.thP.template as<T>();
+        adds.push_back(th);
+      }
+      if (!tf_adds_uploaded_) {
+        CUDA_OK(cudaMemcpyAsync(Tt.upd_adds.p, adds.data(), adds.size() * sizeof(UpdAdd<T>), cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        tf_adds_uploaded_ = true;
+      }
+      a.n_terms = 0;
+      a.n_adds = (int)adds.size();
+    } else {
+      a.n_terms = Tt.n_terms;
+      a.n_adds = Tt.n_adds;
+    }
+    a.terms = Tt.upd_terms.template as<UpdTerm<T>>();
+    a.adds = Tt.upd_adds.template as<UpdAdd<T>>();
+    fused_update<T><<<nblk(Tt.rows_loc, kUpdRows), 256, 0, st>>>(a);
+    ++launches;
+  }
+  bool tf_adds_uploaded_ = false;
+};
+
+template <>
+void Engine<float>::umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g_row0, float* C, int64_t ldc, int M, int K, int k,
+                         cudaStream_t st) {
+  SkinnyParams p;
+  p.C = C;
+  p.ldc = ldc;
+  p.M = M;
+  p.K = K;
+  p.k = k;
+  p.kp = kKp;
+  p.terms = terms_;
+  p.g_row0 = (int)g_row0;
+  // split the reduction so that the grid covers the machine a few times over
+  const int row_blocks = (M + kSkBM - 1) / kSkBM;
+  int ksplit = 1;
+  const int target_ctas = 148 * 2;
+  if (row_blocks < target_ctas) ksplit = std::min((K + 511) / 512, (target_ctas + row_blocks - 1) / row_blocks);
+  ksplit = std::max(1, ksplit);
+  int kps = ((K + ksplit - 1) / ksplit + 63) / 64 * 64;
+  ksplit = (K + kps - 1) / kps;
+  p.k_per_split = kps;
+  p.atomic = ksplit > 1 ? 1 : 0;
+  if (p.atomic) CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st));
+  const CUtensorMap& tx = trans ? r.tmXT : r.tmX;
+  const int N = terms_ * kKp;
+  if (N == 64) { if (trans) umma_launch<64, true>(tx, tg, p, ksplit, st); else umma_launch<64, false>(tx, tg, p, ksplit, st); }
+  else if (N == 128) { if (trans) umma_launch<128, true>(tx, tg, p, ksplit, st); else umma_launch<128, false>(tx, tg, p, ksplit, st); }
+  else { if (trans) umma_launch<192, true>(tx, tg, p, ksplit, st); else umma_launch<192, false>(tx, tg, p, ksplit, st); }
+}
+template <>
+void Engine<double>::umma(RelRec&, bool, const CUtensorMap&, int64_t, double*, int64_t, int, int, int, cudaStream_t) {
+  FZ_THROW(FZ_ERR_UNSUPPORTED, "tensor-core path needs the fp32 engine");
+}
+
+}  // namespace fz
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+struct fz_engine {
+  fz::EngineBase* impl;
+};
+
+#define FZ_GUARD(e, body)                                        \
+  if (!(e) || !(e)->impl) return FZ_ERR_INVALID;                 \
+  try {                                                          \
+    body;                                                        \
+  } catch (const fz::FzError& err_) {                            \
+    (e)->impl->err = err_.msg;                                   \
+    return err_.status;                                          \
+  } catch (const std::exception& ex_) {                          \
+    (e)->impl->err = ex_.what();                                 \
+    return FZ_ERR_INVALID;                                       \
+  }                                                              \
+  return FZ_OK;
+
+extern "C" {
+
+int fz_version(void) { return 100; }
+
+int fz_create(fz_engine** out, int device, int compute) {
+  if (!out) return FZ_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count <= 0) {
+    fz::g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(ce) +
+                         " (this engine has no CPU fallback)";
+    return FZ_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    fz::g_create_error = "device index out of range";
+    return FZ_ERR_INVALID;
+  }
+  ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) {
+    fz::g_create_error = std::string("cudaSetDevice failed: ") + cudaGetErrorString(ce);
+    return FZ_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    fz::g_create_error = "this library is built for sm_100a (Blackwell B200) only; found compute capability " +
+                         std::to_string(prop.major) + "." + std::to_string(prop.minor);
+    return FZ_ERR_UNSUPPORTED;
+  }
+  fz::EngineBase* impl = nullptr;
+  if (compute == FZ_F32) impl = new fz::Engine<float>(device);
+  else if (compute == FZ_F64) impl = new fz::Engine<double>(device);
+  else {
+    fz::g_create_error = "compute dtype must be FZ_F32 or FZ_F64";
+    return FZ_ERR_INVALID;
+  }
+  *out = new fz_engine{impl};
+  return FZ_OK;
+}
+
+int fz_destroy(fz_engine* e) {
+  if (!e) return FZ_OK;
+  delete e->impl;
+  delete e;
+  return FZ_OK;
+}
+
+const char* fz_last_error(const fz_engine* e) {
+  if (!e || !e->impl) return fz::g_create_error.c_str();
+  return e->impl->err.c_str();
+}
+
+int64_t fz_launch_count(const fz_engine* e) { return (e && e->impl) ? e->impl->launches : 0; }
+
+int fz_set_shard(fz_engine* e, int world, int rank) { FZ_GUARD(e, e->impl->set_shard(world, rank)) }
+
+int fz_add_type(fz_engine* e, int64_t n, int k) {
+  if (!e || !e->impl) return FZ_ERR_INVALID;
+  try {
+    return e->impl->add_type(n, k);
+  } catch (const fz::FzError& err_) {
+    e->impl->err = err_.msg;
+    return err_.status;
+  }
+}
+
+int fz_add_relation(fz_engine* e, int ti, int tj, const void* data, int64_t ld, int src, int mem, int storage, int borrow,
+                    const uint8_t* mask, int64_t mask_ld, int mask_mem) {
+  if (!e || !e->impl) return FZ_ERR_INVALID;
+  try {
+    return e->impl->add_relation(ti, tj, data, ld, src, mem, storage, borrow, mask, mask_ld, mask_mem);
+  } catch (const fz::FzError& err_) {
+    e->impl->err = err_.msg;
+    return err_.status;
+  }
+}
+
+int fz_set_factor(fz_engine* e, int t, const void* G0, int64_t ld, int src, int mem) { FZ_GUARD(e, e->impl->set_factor(t, G0, ld, src, mem)) }
+int fz_set_backbone(fz_engine* e, int rel, const void* S, int64_t ld, int src, int mem) { FZ_GUARD(e, e->impl->set_backbone(rel, S, ld, src, mem)) }
+int fz_set_split_terms(fz_engine* e, int terms) { FZ_GUARD(e, e->impl->set_split_terms(terms)) }
+int fz_finalize(fz_engine* e) { FZ_GUARD(e, e->impl->finalize()) }
+int fz_iterate(fz_engine* e, int algo, int n_iters, void* stream) { FZ_GUARD(e, e->impl->iterate(algo, n_iters, (cudaStream_t)stream)) }
+int fz_phase_products(fz_engine* e, int algo, void* stream) { FZ_GUARD(e, e->impl->phase_products(algo, (cudaStream_t)stream)) }
+int fz_phase_update(fz_engine* e, int algo, void* stream) { FZ_GUARD(e, e->impl->phase_update(algo, (cudaStream_t)stream)) }
+int fz_comm_small(fz_engine* e, void** ptr, int64_t* count) { FZ_GUARD(e, e->impl->comm_small(ptr, count)) }
+int fz_comm_bpartial(fz_engine* e, int rel, void** full_ptr, void** local_ptr, int64_t* local_count, int* dtype) {
+  FZ_GUARD(e, e->impl->comm_bpartial(rel, full_ptr, local_ptr, local_count, dtype))
+}
+int fz_comm_factor(fz_engine* e, int t, void** full_ptr, int64_t* local_count, int* dtype) {
+  FZ_GUARD(e, e->impl->comm_factor(t, full_ptr, local_count, dtype))
+}
+int fz_transform_prepare(fz_engine* e, int target, void* stream) { FZ_GUARD(e, e->impl->transform_prepare(target, (cudaStream_t)stream)) }
+int fz_transform_iterate(fz_engine* e, int n_iters, void* stream) { FZ_GUARD(e, e->impl->transform_iterate(n_iters, (cudaStream_t)stream)) }
+int fz_get_factor(fz_engine* e, int t, void* dst, int64_t ld, int dst_dtype, int mem, void* stream) {
+  FZ_GUARD(e, e->impl->get_factor(t, dst, ld, dst_dtype, mem, (cudaStream_t)stream))
+}
+int fz_get_backbone(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int mem, void* stream) {
+  FZ_GUARD(e, e->impl->get_backbone(rel, dst, ld, dst_dtype, mem, (cudaStream_t)stream))
+}
+int fz_objective(fz_engine* e, double* per_relation, double* total, void* stream) {
+  FZ_GUARD(e, e->impl->objective(per_relation, total, (cudaStream_t)stream))
+}
+int fz_complete(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int mem, void* stream) {
+  FZ_GUARD(e, e->impl->complete(rel, dst, ld, dst_dtype, mem, (cudaStream_t)stream))
+}
+
+}  // extern "C"

@@ -1,0 +1,497 @@
+// CUDA-core kernels of the fusion engine (everything that is not the streamed tensor-core product):
+//   gemm_simt        exact fp32 / fp64 tiled products  R*G, R^T*G, Theta(+/-)*G, G*S      (a6, a7, a8)
+//   gram_partial     fp64-accumulated k x k reductions  G^T G  and  G_i^T A_ij            (a5, a6)
+//   fused_update     per-type multiplicative update                                         (a7, a9)
+//   split_factor     fp32 factor -> bf16 split terms (tensor-core operand form)
+//   impute / mask    dfmc re-imputation of unknown entries                                  (a11)
+//   recon_err        ||R - G_i S G_j^T||_F^2                                               (a10)
+// Row references are to SURVEY.md §8(a); file:line citations of the reference are in the engine.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fz {
+
+// numpy.nan_to_num in the compute dtype: NaN -> 0, +-inf -> +-max finite (_dfmf.py:27,255).
+template <class T> struct Lim;
+template <> struct Lim<float> { static __device__ __forceinline__ float max() { return 3.402823466e+38f; } };
+template <> struct Lim<double> { static __device__ __forceinline__ double max() { return 1.7976931348623157e+308; } };
+
+template <class T>
+__device__ __forceinline__ T scrub(T x) {
+  if (x != x) return T(0);
+  if (x > Lim<T>::max()) return Lim<T>::max();
+  if (x < -Lim<T>::max()) return -Lim<T>::max();
+  return x;
+}
+// the reference's literal sign split  t = x > 0;  pos = t*x;  neg = (t-1)*x   (_dfmf.py:256-258)
+template <class T>
+__device__ __forceinline__ void sign_split(T x, T& pos, T& neg) {
+  const T t = (x > T(0)) ? T(1) : T(0);
+  pos = t * x;
+  neg = (t - T(1)) * x;
+}
+
+template <class XT, class T> __device__ __forceinline__ T load_as(const XT* p) { return static_cast<T>(*p); }
+template <> __device__ __forceinline__ float load_as<__nv_bfloat16, float>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ double load_as<__nv_bfloat16, double>(const __nv_bfloat16* p) { return (double)__bfloat162float(*p); }
+
+// ------------------------------------------------------------------------------------------------
+// C[M x N] (+)= op(X) * Y      op(X) = X (M x K, row-major)  or  X^T (X is K x M, row-major)
+// kSplit: two outputs  C += max(X,0)*Y,  C2 += max(-X,0)*Y   (constraint matrices, _dfmf.py:203-208)
+// ------------------------------------------------------------------------------------------------
+constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16;
+
+template <class T, class XT, bool kTrans, bool kSplit>
+__global__ void __launch_bounds__(256)
+gemm_simt(const XT* __restrict__ X, long long ldx, const T* __restrict__ Y, long long ldy, T* __restrict__ C,
+          T* __restrict__ C2, long long ldc, int M, int N, int K, int accumulate) {
+  __shared__ T Xs[kGemmBK][kGemmBM + 4];
+  __shared__ T Xn[kSplit ? kGemmBK : 1][kSplit ? kGemmBM + 4 : 1];
+  __shared__ T Ys[kGemmBK][kGemmBN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * kGemmBN;
+  const int ty = tid / 16, tx = tid % 16;
+  T acc[4][4], acc2[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j] = T(0); acc2[i][j] = T(0); }
+
+  for (int k0 = 0; k0 < K; k0 += kGemmBK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      int mm, kk;
+      if (!kTrans) { mm = idx / kGemmBK; kk = idx % kGemmBK; }
+      else         { kk = idx / kGemmBM; mm = idx % kGemmBM; }
+      T v = T(0);
+      if (m0 + mm < M && k0 + kk < K)
+        v = kTrans ? load_as<XT, T>(X + (long long)(k0 + kk) * ldx + (m0 + mm))
+                   : load_as<XT, T>(X + (long long)(m0 + mm) * ldx + (k0 + kk));
+      if (kSplit) { T p, n; sign_split(v, p, n); Xs[kk][mm] = p; Xn[kk][mm] = n; }
+      else Xs[kk][mm] = v;
+      const int yk = idx / kGemmBN, yn = idx % kGemmBN;
+      T w = T(0);
+      if (k0 + yk < K && n0 + yn < N) w = Y[(long long)(k0 + yk) * ldy + (n0 + yn)];
+      Ys[yk][yn] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kGemmBK; ++kk) {
+      T a[4], b[4], a2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = Xs[kk][ty * 4 + i]; if (kSplit) a2[i] = Xn[kk][ty * 4 + i]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ys[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] += a[i] * b[j];
+          if (kSplit) acc2[i][j] += a2[i] * b[j];
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      const long long o = (long long)m * ldc + n;
+      C[o] = accumulate ? C[o] + acc[i][j] : acc[i][j];
+      if (kSplit) C2[o] = accumulate ? C2[o] + acc2[i][j] : acc2[i][j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// part[chunk][ka][kb] = sum over the chunk's rows of X[r][a] * Y[r][b], accumulated in fp64 from the
+// exact products of the stored values (F7: the k x k chain must not see fp32 reduction error).
+// grid = (chunks, ceil(ka/64), ceil(kb/64)), 256 threads, 4x4 outputs per thread.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+gram_partial(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, long long ldy, double* __restrict__ part,
+             long long n_rows, int ka, int kb, int rows_per_chunk, int scrub_inputs) {
+  __shared__ double Xs[16][64 + 2];
+  __shared__ double Ys[16][64 + 2];
+  const int tid = threadIdx.x;
+  const int a0 = blockIdx.y * 64, b0 = blockIdx.z * 64;
+  const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
+  const long long r_end = min(n_rows, r_begin + rows_per_chunk);
+  const int ty = tid / 16, tx = tid % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      const int rr = idx / 64, cc = idx % 64;
+      double xv = 0.0, yv = 0.0;
+      if (r0 + rr < r_end) {
+        if (a0 + cc < ka) xv = (double)X[(r0 + rr) * ldx + a0 + cc];
+        if (b0 + cc < kb) yv = (double)Y[(r0 + rr) * ldy + b0 + cc];
+        if (scrub_inputs) { xv = scrub(xv); yv = scrub(yv); }
+      }
+      Xs[rr][cc] = xv;
+      Ys[rr][cc] = yv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Xs[rr][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ys[rr][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+  double* out = part + (long long)blockIdx.x * ka * kb;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = a0 + ty * 4 + i;
+    if (a >= ka) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = b0 + tx * 4 + j;
+      if (b < kb) out[(long long)a * kb + b] = acc[i][j];
+    }
+  }
+}
+
+// out[i] = sum_c part[c][i]  in fixed chunk order (deterministic)
+__global__ void reduce_partials(const double* __restrict__ part, double* __restrict__ out, int n_chunks, long long elems) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= elems) return;
+  double s = 0.0;
+  for (int c = 0; c < n_chunks; ++c) s += part[(long long)c * elems + i];
+  out[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused per-type multiplicative update (reference _dfmf.py:246-296):
+//   num = sum_terms pos(X_r W_r) + G Nsum + sum_add addN ;  den = sum_terms neg(X_r W_r) + G Dsum + sum_add addD
+//   Gnew = G * sqrt(num / max(den, eps64))
+// A "term" is one incident relation: X_r = A_ij (rows of this type) with W_r = S_ij^T, or X_r = B_ij with
+// W_r = S_ij.  Nsum/Dsum are the per-type sums of the negative/positive parts of S G^T G S^T (k x k).
+// Additive pairs carry the constraint products (Theta^- G, Theta^+ G) or transform's frozen terms.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+struct UpdTerm {
+  const T* X;      // rows x kx
+  long long ldx;
+  const T* W;      // kx x kt, row-major
+  int kx;
+  int pad_;
+};
+template <class T>
+struct UpdAdd {
+  const T* num;    // rows x kt (ld = kt)
+  const T* den;
+};
+template <class T>
+struct UpdArgs {
+  const T* G;      // rows x kt (old factor, local rows)
+  T* Gnew;
+  long long ldg;
+  long long rows;
+  int kt;
+  int n_terms;
+  int n_adds;
+  int scrub_terms;  // dfmf: nan_to_num on tmp1/tmp4 (and on the k x k terms upstream); dfmc/transform: no
+  const UpdTerm<T>* terms;
+  const UpdAdd<T>* adds;
+  const T* Nsum;   // kt x kt
+  const T* Dsum;
+};
+
+constexpr int kUpdRows = 32;
+
+constexpr int kUpdSlab = 32;   // reduction slab (keeps fp64 tiles under the 48 KB static limit)
+
+template <class T>
+__global__ void __launch_bounds__(256)
+fused_update(const UpdArgs<T> a) {
+  __shared__ T Xs[kUpdRows][kUpdSlab + 1];
+  __shared__ T Ws[kUpdSlab][64 + 1];
+  __shared__ T Ws2[kUpdSlab][64 + 1];
+  const int tid = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * kUpdRows;
+  const int r = tid / 8;            // row inside the block (0..31)
+  const int qb = tid % 8;           // this thread's outputs: q = q0 + qb + 8*j, j = 0..7
+  const long long row = r0 + r;
+  const T eps = (T)2.220446049250313e-16;
+
+  for (int q0 = 0; q0 < a.kt; q0 += 64) {
+    T num[8], den[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { num[j] = T(0); den[j] = T(0); }
+
+    // ---- relation terms: pos/neg parts of X W
+    for (int t = 0; t < a.n_terms; ++t) {
+      const UpdTerm<T> term = a.terms[t];
+      T acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = T(0);
+      for (int c0 = 0; c0 < term.kx; c0 += kUpdSlab) {
+        for (int idx = tid; idx < kUpdRows * kUpdSlab; idx += 256) {
+          const int rr = idx / kUpdSlab, cc = idx % kUpdSlab;
+          T v = T(0);
+          if (r0 + rr < a.rows && c0 + cc < term.kx) v = term.X[(r0 + rr) * term.ldx + c0 + cc];
+          Xs[rr][cc] = v;
+        }
+        for (int idx = tid; idx < kUpdSlab * 64; idx += 256) {
+          const int cc = idx / 64, qq = idx % 64;
+          T v = T(0);
+          if (c0 + cc < term.kx && q0 + qq < a.kt) v = term.W[(long long)(c0 + cc) * a.kt + q0 + qq];
+          Ws[cc][qq] = v;
+        }
+        __syncthreads();
+        const int cmax = min(kUpdSlab, term.kx - c0);
+        for (int cc = 0; cc < cmax; ++cc) {
+          const T x = Xs[r][cc];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += x * Ws[cc][qb + 8 * j];
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        T v = acc[j];
+        if (a.scrub_terms) v = scrub(v);
+        T p, n;
+        sign_split(v, p, n);
+        num[j] += p;
+        den[j] += n;
+      }
+    }
+    // ---- G * Nsum and G * Dsum
+    for (int c0 = 0; c0 < a.kt; c0 += kUpdSlab) {
+      for (int idx = tid; idx < kUpdRows * kUpdSlab; idx += 256) {
+        const int rr = idx / kUpdSlab, cc = idx % kUpdSlab;
+        T v = T(0);
+        if (r0 + rr < a.rows && c0 + cc < a.kt) v = a.G[(r0 + rr) * a.ldg + c0 + cc];
+        Xs[rr][cc] = v;
+      }
+      for (int idx = tid; idx < kUpdSlab * 64; idx += 256) {
+        const int cc = idx / 64, qq = idx % 64;
+        T v = T(0), w = T(0);
+        if (c0 + cc < a.kt && q0 + qq < a.kt) {
+          v = a.Nsum[(long long)(c0 + cc) * a.kt + q0 + qq];
+          w = a.Dsum[(long long)(c0 + cc) * a.kt + q0 + qq];
+        }
+        Ws[cc][qq] = v;
+        Ws2[cc][qq] = w;
+      }
+      __syncthreads();
+      const int cmax = min(kUpdSlab, a.kt - c0);
+      for (int cc = 0; cc < cmax; ++cc) {
+        const T x = Xs[r][cc];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          num[j] += x * Ws[cc][qb + 8 * j];
+          den[j] += x * Ws2[cc][qb + 8 * j];
+        }
+      }
+      __syncthreads();
+    }
+    // ---- additive pairs + the update itself
+    if (row < a.rows) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int q = q0 + qb + 8 * j;
+        if (q >= a.kt) continue;
+        T nu = num[j], de = den[j];
+        for (int s = 0; s < a.n_adds; ++s) {
+          nu += a.adds[s].num[row * a.kt + q];
+          de += a.adds[s].den[row * a.kt + q];
+        }
+        const T g = a.G[row * a.ldg + q];
+        a.Gnew[row * a.ldg + q] = g * sqrt(nu / max(de, eps));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Factor -> tensor-core operand form: Gs[r][t*kp + q] = bf16 term t of the running residual of G[r][q].
+// Rows >= n_valid and columns >= k are zero.  (Own design: no counterpart in the reference.)
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void split_factor(const T* __restrict__ G, long long ldg, __nv_bfloat16* __restrict__ Gs, long long n_valid,
+                             long long n_pad, int k, int kp, int terms) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * kp) return;
+  const long long r = idx / kp;
+  const int q = (int)(idx % kp);
+  float v = 0.f;
+  if (r < n_valid && q < k) v = (float)G[r * ldg + q];
+  __nv_bfloat16* out = Gs + r * (long long)(kp * terms) + q;
+  for (int t = 0; t < terms; ++t) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[(long long)t * kp] = h;
+    v -= __bfloat162float(h);
+  }
+}
+
+// dst[r][c] = (DT) src[r][c]   (dtype / layout conversion of uploaded and downloaded matrices)
+template <class ST, class DT>
+__global__ void convert_2d(const ST* __restrict__ src, long long lds, DT* __restrict__ dst, long long ldd, long long rows,
+                           long long cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols, c = idx % cols;
+  dst[r * ldd + c] = static_cast<DT>(src[r * lds + c]);
+}
+template <class ST>
+__global__ void convert_2d_to_bf16(const ST* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
+                                   long long rows, long long cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols, c = idx % cols;
+  dst[r * ldd + c] = __float2bfloat16_rn((float)src[r * lds + c]);
+}
+template <class DT>
+__global__ void convert_2d_from_bf16(const __nv_bfloat16* __restrict__ src, long long lds, DT* __restrict__ dst, long long ldd,
+                                     long long rows, long long cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols, c = idx % cols;
+  dst[r * ldd + c] = (DT)__bfloat162float(src[r * lds + c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dfmc: R[mask] = 0 before the first iteration (_dfmc.py:287-292) and
+//       R[mask] = (G_i S G_j^T)[mask] after every S-update (_dfmc.py:319-325);  T1 = G_i S is given.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void mask_zero(T* __restrict__ R, long long ld, const uint8_t* __restrict__ mask, long long mld, long long rows,
+                          long long cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols, c = idx % cols;
+  if (mask[r * mld + c]) R[r * ld + c] = T(0);
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+impute_masked(T* __restrict__ R, long long ld, const uint8_t* __restrict__ mask, long long mld, const T* __restrict__ T1,
+              long long ldt, const T* __restrict__ Gj, long long ldg, long long rows, long long cols, int kj) {
+  __shared__ T Ts[32][32 + 1];
+  __shared__ T Gsm[32][32 + 1];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // ty 0..7, 4 rows each
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+  T acc[4] = {T(0), T(0), T(0), T(0)};
+  for (int q0 = 0; q0 < kj; q0 += 32) {
+    for (int e = 0; e < 4; ++e) {
+      const int rr = ty * 4 + e;
+      T a = T(0), b = T(0);
+      if (r0 + rr < rows && q0 + tx < kj) a = T1[(r0 + rr) * ldt + q0 + tx];
+      if (c0 + rr < cols && q0 + tx < kj) b = Gj[(c0 + rr) * ldg + q0 + tx];
+      Ts[rr][tx] = a;
+      Gsm[rr][tx] = b;
+    }
+    __syncthreads();
+    const int qmax = min(32, kj - q0);
+    for (int q = 0; q < qmax; ++q) {
+      const T g = Gsm[tx][q];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] += Ts[ty * 4 + e][q] * g;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const long long r = r0 + ty * 4 + e, c = c0 + tx;
+    if (r < rows && c < cols && mask[r * mld + c]) R[r * ld + c] = acc[e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[0] += sum over the tile of (R - T1 Gj^T)^2   (fp64 accumulation; _dfmf.py:306-319)
+// optionally also writes the reconstruction (complete(), base.py:119-146)
+// ------------------------------------------------------------------------------------------------
+template <class T, class XT>
+__global__ void __launch_bounds__(256)
+recon_err(const XT* __restrict__ R, long long ld, const T* __restrict__ T1, long long ldt, const T* __restrict__ Gj,
+          long long ldg, long long rows, long long cols, int kj, double* __restrict__ out_sq, T* __restrict__ recon,
+          long long ldr) {
+  __shared__ T Ts[32][32 + 1];
+  __shared__ T Gsm[32][32 + 1];
+  __shared__ double red[256];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+  T acc[4] = {T(0), T(0), T(0), T(0)};
+  for (int q0 = 0; q0 < kj; q0 += 32) {
+    for (int e = 0; e < 4; ++e) {
+      const int rr = ty * 4 + e;
+      T a = T(0), b = T(0);
+      if (r0 + rr < rows && q0 + tx < kj) a = T1[(r0 + rr) * ldt + q0 + tx];
+      if (c0 + rr < cols && q0 + tx < kj) b = Gj[(c0 + rr) * ldg + q0 + tx];
+      Ts[rr][tx] = a;
+      Gsm[rr][tx] = b;
+    }
+    __syncthreads();
+    const int qmax = min(32, kj - q0);
+    for (int q = 0; q < qmax; ++q) {
+      const T g = Gsm[tx][q];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] += Ts[ty * 4 + e][q] * g;
+    }
+    __syncthreads();
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const long long r = r0 + ty * 4 + e, c = c0 + tx;
+    if (r < rows && c < cols) {
+      if (recon) recon[r * ldr + c] = acc[e];
+      if (R) {
+        const double d = (double)load_as<XT, T>(R + r * ld + c) - (double)acc[e];
+        s += d * d;
+      }
+    }
+  }
+  if (out_sq) {
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+      if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out_sq, red[0]);
+  }
+}
+
+// num += pos(C), den += neg(C)  (transform: frozen relation terms, _dfmf.py:394-419; no scrub there)
+template <class T>
+__global__ void accum_sign_split(const T* __restrict__ C, T* __restrict__ num, T* __restrict__ den, long long elems) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= elems) return;
+  T p, n;
+  sign_split(C[i], p, n);
+  num[i] += p;
+  den[i] += n;
+}
+
+template <class T>
+__global__ void fill_value(T* p, long long n, T v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace fz

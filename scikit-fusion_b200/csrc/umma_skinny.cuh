@@ -24,9 +24,7 @@ namespace fz {
 
 struct SkinnyParams {
   float* C;            // output base
-  long long ldc;       // elements between consecutive rows inside a chunk
-  long long rows_per_chunk;  // rows per contiguous chunk (row-sharded layouts); >= M for a plain matrix
-  long long chunk_stride;    // elements between chunk bases
+  long long ldc;       // elements between consecutive rows of C
   int M;               // rows of C  (rows of X, or columns of X when transposed)
   int K;               // reduction length (columns of X, or rows of X when transposed)
   int k;               // valid output columns (<= kp)
@@ -34,6 +32,7 @@ struct SkinnyParams {
   int terms;           // number of split terms (N = terms * kp)
   int k_per_split;     // reduction elements handled per blockIdx.y (multiple of 64)
   int atomic;          // 1: red.add into C (split-K), 0: plain store
+  int g_row0;          // first row of Gs that pairs with reduction index 0 (row-sharded factors)
 };
 
 constexpr int kSkBM = 128;   // rows of C per CTA == UMMA M
@@ -107,7 +106,7 @@ umma_skinny_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
 #pragma unroll
         for (int ch = 0; ch < N / 64; ++ch)
-          ptx::tma_load_2d(gs + ch * 8192, &tmG, &full_bar[s], ch * 64, k0, ptx::kEvictLast);
+          ptx::tma_load_2d(gs + ch * 8192, &tmG, &full_bar[s], ch * 64, p.g_row0 + k0, ptx::kEvictLast);
       }
     }
   } else if (warp == 1) {
@@ -140,11 +139,7 @@ umma_skinny_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
     float* crow = nullptr;
-    if (row < p.M) {
-      const long long chunk = row / p.rows_per_chunk;
-      const long long within = row - chunk * p.rows_per_chunk;
-      crow = p.C + chunk * p.chunk_stride + within * p.ldc;
-    }
+    if (row < p.M) crow = p.C + (long long)row * p.ldc;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     for (int q0 = 0; q0 < p.kp; q0 += 32) {
       float acc[32], v[32];

@@ -1,0 +1,276 @@
+"""ctypes binding of include/fz_fusion.h (libfz_fusion.so) -- the only door to the GPU.
+
+There is deliberately no CPU fallback: if the library or a B200 is missing, calls raise
+``EngineUnavailable`` with the reason.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(_HERE)                      # scikit-fusion_b200/
+LIB_PATH = os.path.join(PKG_ROOT, "libfz_fusion.so")
+CSRC = os.path.join(PKG_ROOT, "csrc")
+
+FZ_F64, FZ_F32, FZ_BF16, FZ_U8 = 0, 1, 2, 3
+FZ_HOST, FZ_DEVICE = 0, 1
+FZ_DFMF, FZ_DFMC = 0, 1
+
+# every symbol include/fz_fusion.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "fz_create", "fz_destroy", "fz_last_error", "fz_version", "fz_launch_count", "fz_set_shard", "fz_add_type",
+    "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_finalize", "fz_iterate",
+    "fz_phase_products", "fz_phase_update", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
+    "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete",
+]
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def nvcc_command(out=LIB_PATH):
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+            "-Xcompiler", "-fPIC", "-o", out, os.path.join(CSRC, "fz_engine.cu")]
+
+
+def build(force=False, verbose=False):
+    """Compile libfz_fusion.so in-tree for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs.append(os.path.join(os.path.dirname(PKG_ROOT), "include", "fz_fusion.h"))
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs if os.path.exists(s))):
+        return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise EngineUnavailable("nvcc failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineUnavailable(
+            "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+    i64, i32, vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
+    sig = {
+        "fz_create": (i32, [c_void_pp, i32, i32]),
+        "fz_destroy": (i32, [vp]),
+        "fz_last_error": (ctypes.c_char_p, [vp]),
+        "fz_version": (i32, []),
+        "fz_launch_count": (i64, [vp]),
+        "fz_set_shard": (i32, [vp, i32, i32]),
+        "fz_add_type": (i32, [vp, i64, i32]),
+        "fz_add_relation": (i32, [vp, i32, i32, vp, i64, i32, i32, i32, i32, vp, i64, i32]),
+        "fz_set_factor": (i32, [vp, i32, vp, i64, i32, i32]),
+        "fz_set_backbone": (i32, [vp, i32, vp, i64, i32, i32]),
+        "fz_set_split_terms": (i32, [vp, i32]),
+        "fz_finalize": (i32, [vp]),
+        "fz_iterate": (i32, [vp, i32, i32, vp]),
+        "fz_phase_products": (i32, [vp, i32, vp]),
+        "fz_phase_update": (i32, [vp, i32, vp]),
+        "fz_comm_small": (i32, [vp, c_void_pp, ctypes.POINTER(i64)]),
+        "fz_comm_bpartial": (i32, [vp, i32, c_void_pp, c_void_pp, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
+        "fz_comm_factor": (i32, [vp, i32, c_void_pp, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
+        "fz_transform_prepare": (i32, [vp, i32, vp]),
+        "fz_transform_iterate": (i32, [vp, i32, vp]),
+        "fz_get_factor": (i32, [vp, i32, vp, i64, i32, i32, vp]),
+        "fz_get_backbone": (i32, [vp, i32, vp, i64, i32, i32, vp]),
+        "fz_objective": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]),
+        "fz_complete": (i32, [vp, i32, vp, i64, i32, i32, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+_NP2FZ = {np.dtype(np.float64): FZ_F64, np.dtype(np.float32): FZ_F32, np.dtype(np.uint8): FZ_U8,
+          np.dtype(np.bool_): FZ_U8}
+_DTYPE_NAMES = {"float64": FZ_F64, "float32": FZ_F32, "bfloat16": FZ_BF16, "f64": FZ_F64, "f32": FZ_F32,
+                "bf16": FZ_BF16}
+
+
+def dtype_code(name):
+    if isinstance(name, int):
+        return name
+    try:
+        return _DTYPE_NAMES[str(name).replace("torch.", "")]
+    except KeyError:
+        raise ValueError("unknown dtype %r (float64 | float32 | bfloat16)" % (name,))
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def _describe(x, allow_mask=False):
+    """-> (keepalive, pointer, ld, dtype code, mem) for a 2-D numpy array or torch CUDA tensor."""
+    if _is_torch_cuda(x):
+        if x.dim() != 2 or x.stride(1) != 1:
+            raise ValueError("device matrices must be 2-D with unit inner stride")
+        code = dtype_code(str(x.dtype)) if str(x.dtype) != "torch.uint8" else FZ_U8
+        if str(x.dtype) == "torch.bool":
+            code = FZ_U8
+        return x, ctypes.c_void_p(x.data_ptr()), int(x.stride(0)), code, FZ_DEVICE
+    a = np.asarray(x)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D matrix, got shape %r" % (a.shape,))
+    if a.dtype not in _NP2FZ:
+        a = a.astype(np.float64)
+    a = np.ascontiguousarray(a)
+    return a, ctypes.c_void_p(a.ctypes.data), int(a.shape[1]) if a.shape[1] else 1, _NP2FZ[a.dtype], FZ_HOST
+
+
+class Engine(object):
+    """Thin RAII wrapper of one fz_engine handle."""
+
+    def __init__(self, device=0, compute="float32"):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        self.compute = dtype_code(compute)
+        rc = self._L.fz_create(ctypes.byref(self._h), int(device), self.compute)
+        if rc != 0:
+            msg = self._L.fz_last_error(None).decode()
+            self._h = ctypes.c_void_p()
+            raise EngineUnavailable("fz_create failed (%d): %s" % (rc, msg))
+        self._keep = []
+        self.type_shape = []     # (n, k) per type id
+        self.rel_types = []      # (ti, tj) per relation id
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.fz_destroy(self._h)
+            self._h = ctypes.c_void_p()
+        self._keep = []
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise EngineError("engine error %d: %s" % (rc, self._L.fz_last_error(self._h).decode()))
+        return rc
+
+    # ---- description
+    def set_shard(self, world, rank):
+        self._ck(self._L.fz_set_shard(self._h, world, rank))
+
+    def add_type(self, n, k):
+        tid = self._ck(self._L.fz_add_type(self._h, int(n), int(k)))
+        self.type_shape.append((int(n), int(k)))
+        return tid
+
+    def add_relation(self, ti, tj, data, storage=None, borrow=False, mask=None):
+        keep, ptr, ld, code, mem = _describe(data)
+        st = code if storage is None else dtype_code(storage)
+        if st == FZ_U8:
+            raise ValueError("relation data cannot be uint8")
+        mkeep, mptr, mld, mmem = None, None, 0, FZ_HOST
+        if mask is not None:
+            if not _is_torch_cuda(mask):
+                mask = np.ascontiguousarray(np.asarray(mask, dtype=np.uint8))
+            mkeep, mptr, mld, _mc, mmem = _describe(mask)
+        rid = self._ck(self._L.fz_add_relation(self._h, ti, tj, ptr, ld, code, mem, st, 1 if borrow else 0, mptr, mld, mmem))
+        if borrow:
+            self._keep.append(keep)
+        self.rel_types.append((ti, tj))
+        return rid
+
+    def set_factor(self, t, G0):
+        keep, ptr, ld, code, mem = _describe(G0)
+        self._ck(self._L.fz_set_factor(self._h, t, ptr, ld, code, mem))
+
+    def set_backbone(self, rel, S):
+        keep, ptr, ld, code, mem = _describe(S)
+        self._ck(self._L.fz_set_backbone(self._h, rel, ptr, ld, code, mem))
+
+    def set_split_terms(self, terms):
+        self._ck(self._L.fz_set_split_terms(self._h, int(terms)))
+
+    def finalize(self):
+        self._ck(self._L.fz_finalize(self._h))
+
+    # ---- loop
+    def iterate(self, algo, n_iters, stream=0):
+        self._ck(self._L.fz_iterate(self._h, algo, int(n_iters), ctypes.c_void_p(stream)))
+
+    def phase_products(self, algo, stream=0):
+        self._ck(self._L.fz_phase_products(self._h, algo, ctypes.c_void_p(stream)))
+
+    def phase_update(self, algo, stream=0):
+        self._ck(self._L.fz_phase_update(self._h, algo, ctypes.c_void_p(stream)))
+
+    def transform_prepare(self, target, stream=0):
+        self._ck(self._L.fz_transform_prepare(self._h, target, ctypes.c_void_p(stream)))
+
+    def transform_iterate(self, n_iters, stream=0):
+        self._ck(self._L.fz_transform_iterate(self._h, int(n_iters), ctypes.c_void_p(stream)))
+
+    def comm_small(self):
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        self._ck(self._L.fz_comm_small(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def comm_bpartial(self, rel):
+        f, l, n, d = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int()
+        self._ck(self._L.fz_comm_bpartial(self._h, rel, ctypes.byref(f), ctypes.byref(l), ctypes.byref(n), ctypes.byref(d)))
+        return f.value, l.value, n.value, d.value
+
+    def comm_factor(self, t):
+        f, n, d = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int()
+        self._ck(self._L.fz_comm_factor(self._h, t, ctypes.byref(f), ctypes.byref(n), ctypes.byref(d)))
+        return f.value, n.value, d.value
+
+    # ---- results (float64 numpy, like the reference returns)
+    def get_factor(self, t, stream=0):
+        if not 0 <= t < len(self.type_shape):
+            raise EngineError("unknown type id %r" % (t,))
+        n, k = self.type_shape[t]
+        out = np.empty((n, k), dtype=np.float64)
+        self._ck(self._L.fz_get_factor(self._h, t, ctypes.c_void_p(out.ctypes.data), k, FZ_F64, FZ_HOST, ctypes.c_void_p(stream)))
+        return out
+
+    def get_backbone(self, rel, stream=0):
+        if not 0 <= rel < len(self.rel_types):
+            raise EngineError("unknown relation id %r" % (rel,))
+        ti, tj = self.rel_types[rel]
+        ki, kj = self.type_shape[ti][1], self.type_shape[tj][1]
+        out = np.empty((ki, kj), dtype=np.float64)
+        self._ck(self._L.fz_get_backbone(self._h, rel, ctypes.c_void_p(out.ctypes.data), kj, FZ_F64, FZ_HOST, ctypes.c_void_p(stream)))
+        return out
+
+    def objective(self, n_relations, stream=0):
+        per = (ctypes.c_double * max(1, n_relations))()
+        tot = ctypes.c_double()
+        self._ck(self._L.fz_objective(self._h, per, ctypes.byref(tot), ctypes.c_void_p(stream)))
+        return tot.value, list(per)[:n_relations]
+
+    def complete(self, rel, stream=0):
+        ti, tj = self.rel_types[rel]
+        ni, nj = self.type_shape[ti][0], self.type_shape[tj][0]
+        out = np.empty((ni, nj), dtype=np.float64)
+        self._ck(self._L.fz_complete(self._h, rel, ctypes.c_void_p(out.ctypes.data), nj, FZ_F64, FZ_HOST, ctypes.c_void_p(stream)))
+        return out
+
+    @property
+    def launches(self):
+        return int(self._L.fz_launch_count(self._h))

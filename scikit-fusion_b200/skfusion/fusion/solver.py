@@ -1,0 +1,252 @@
+"""dfmf / dfmc / transform -- the drop-in seam, same signatures as the reference free functions
+(skfusion/fusion/decomposition/_dfmf.py:127, _dfmc.py:181, _dfmf.py:330), executed on a B200.
+
+Host work kept here: counting objects, seeding the factors with numpy's RandomState (bit-exact RNG
+consumption, initializers.py), early-stopping bookkeeping, logging, the user callback.  Everything
+inside ``for iter in range(max_iter)`` runs in the CUDA engine (include/fz_fusion.h); without a
+callback / error tracking the whole loop is ONE C call with no host round trips.
+
+Engine-only keyword arguments (all optional, see options.py): device, dtype, storage, split_terms.
+Relation matrices may be numpy arrays (copied to the GPU) or torch CUDA tensors (used in place when
+their dtype equals the storage dtype).
+"""
+import logging
+
+import numpy as np
+
+from .. import _capi
+from .initializers import initialize
+from .options import resolve
+
+log = logging.getLogger("skfusion.fusion")
+
+
+def count_objects(obj_types, R):
+    """Objects per type from the relation shapes; the first shape seen wins and mismatches are only
+    logged (reference _dfmf.py:95-124)."""
+    sizes = {}
+    for (row_t, col_t), mats in R.items():
+        for mat in mats:
+            for axis, obj_type in enumerate((row_t, col_t)):
+                seen = sizes.setdefault(obj_type, mat.shape[axis])
+                if seen != mat.shape[axis]:
+                    log.critical("Relation matrix R_(%s,%s) dimension mismatch" % (row_t, col_t))
+    if set(obj_types) != set(sizes.keys()):
+        log.critical("Object type specification mismatch")
+    return sizes
+
+
+def _configure_logging(verbose):
+    logging.basicConfig(format="%(asctime)s %(levelname)s: %(message)s", datefmt="%m/%d/%Y %I:%M:%S %p",
+                        level=50 - verbose)
+
+
+class _Problem(object):
+    """One engine handle plus the id maps between the reference's dict keys and engine ids."""
+
+    def __init__(self, opts):
+        self.opts = opts
+        self.engine = _capi.Engine(device=opts["device"], compute=opts["dtype"])
+        if opts.get("split_terms"):
+            self.engine.set_split_terms(opts["split_terms"])
+        self.type_id = {}
+        self.type_order = []
+        self.rel_ids = {}          # (ti, tj) -> [relation id per parallel relation]
+
+    def add_types(self, obj_types, sizes, ranks):
+        for t in obj_types:
+            self.type_id[t] = self.engine.add_type(sizes[t], int(ranks[t]))
+            self.type_order.append(t)
+
+    def add_blocks(self, R, Theta, M=None):
+        storage = self.opts.get("storage")
+        for key, mats in R.items():
+            ids = []
+            for l, mat in enumerate(mats):
+                mask = None
+                if M is not None and M.get(key) is not None:
+                    mask = M[key][l]
+                ids.append(self.engine.add_relation(self.type_id[key[0]], self.type_id[key[1]], mat,
+                                                    storage=storage, borrow=self._can_borrow(mat, storage, mask),
+                                                    mask=mask))
+            self.rel_ids[key] = ids
+        for key, mats in Theta.items():
+            for mat in mats:
+                self.engine.add_relation(self.type_id[key[0]], self.type_id[key[1]], mat, storage=None)
+
+    def _can_borrow(self, mat, storage, mask):
+        if mask is not None or not _capi._is_torch_cuda(mat):
+            return False
+        want = _capi.dtype_code(storage) if storage else self.engine.compute
+        return _capi.dtype_code(str(mat.dtype)) == want and (want != _capi.FZ_BF16 or mat.stride(0) % 8 == 0)
+
+    def factors(self):
+        return {(t, t): self.engine.get_factor(self.type_id[t]) for t in self.type_order}
+
+    def backbones(self):
+        return {key: [self.engine.get_backbone(i) for i in ids] for key, ids in self.rel_ids.items()}
+
+    def n_relations(self):
+        return sum(len(v) for v in self.rel_ids.values())
+
+    def relation_index(self, key, l):
+        """Position of relation (key, l) in the engine's objective vector (insertion order)."""
+        pos = 0
+        for k, ids in self.rel_ids.items():
+            if k == key:
+                return pos + l
+            pos += len(ids)
+        raise KeyError(key)
+
+    def close(self):
+        self.engine.close()
+
+
+def _fit(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopping, stopping_system, verbose,
+         compute_err, callback, random_state, engine_kwargs):
+    _configure_logging(verbose)
+    opts = resolve(**engine_kwargs)
+    sizes = count_objects(obj_types, R)
+    first = {key: _host_view(mats[0]) for key, mats in R.items()} if init_type != "random" else {}
+    G0 = initialize(obj_types, sizes, obj_type2rank, first, init_type, random_state)
+    if stopping_system:
+        compute_err = True
+
+    prob = _Problem(opts)
+    try:
+        prob.add_types(obj_types, sizes, obj_type2rank)
+        prob.add_blocks(R, Theta, M)
+        for t in obj_types:
+            prob.engine.set_factor(prob.type_id[t], G0[t, t])
+        prob.engine.finalize()
+
+        interactive = bool(stopping or compute_err or callback)
+        if not interactive:
+            if max_iter > 0:
+                prob.engine.iterate(algo, max_iter)
+                return prob.factors(), prob.backbones()
+            return G0, None
+
+        err_target, err_system, history = (None, None), (None, None), []
+        G, S = G0, None
+        for it in range(max_iter):
+            if it > 1 and stopping and err_target[1] - err_target[0] < stopping[1]:
+                log.info("Early stopping: target matrix change < %5.4f" % stopping[1])
+                break
+            if it > 1 and stopping_system and err_system[1] - err_system[0] < stopping_system:
+                log.info("Early stopping: matrix system change < %5.4f" % stopping_system)
+                break
+            log.info("Factorization iteration: %d" % it)
+            prob.engine.iterate(algo, 1)
+            if stopping or compute_err:
+                total, per_rel = prob.engine.objective(prob.n_relations())
+                if stopping:
+                    tkey, tl = _target_of(stopping)
+                    err_target = (per_rel[prob.relation_index(tkey, tl)], err_target[0])
+                if compute_err:
+                    log.info("Error (objective function value): %5.4f" % total)
+                    history.append(total)
+                    if stopping_system:
+                        err_system = (total, err_system[0])
+            if callback:
+                G, S = prob.factors(), prob.backbones()
+                callback(G, S, it)
+        if compute_err and history:
+            log.info("Violations of optimization objective: %d/%d " % (int(np.sum(np.diff(history) > 0)), len(history)))
+        if max_iter > 0:
+            G, S = prob.factors(), prob.backbones()
+        return G, S
+    finally:
+        prob.close()
+
+
+def _target_of(stopping):
+    """``stopping`` is ((key, l), eps) in dfmc (_dfmc.py:370-374); dfmf's (key, eps) form indexes the
+    relation list as an array upstream (_dfmf.py:303-304) -- accepted here as relation 0."""
+    target = stopping[0]
+    if len(target) == 2 and isinstance(target[0], tuple):
+        return target[0], target[1]
+    return target, 0
+
+
+def _host_view(mat):
+    if _capi._is_torch_cuda(mat):
+        return mat.float().cpu().numpy().astype(np.float64)
+    return mat
+
+
+def dfmf(R, Theta, obj_types, obj_type2rank, max_iter=10, init_type="random_vcol", stopping=None, stopping_system=None,
+         verbose=0, compute_err=False, callback=None, random_state=None, n_jobs=1, **engine_kwargs):
+    """Data fusion by matrix factorization.  Returns (G, S): G[(t,t)] is n_t x k_t, S[(ti,tj)] a list
+    of k_i x k_j backbones, one per parallel relation.  ``n_jobs`` is accepted and ignored (the GPU
+    engine replaces the joblib fan-out of _dfmf.py:69-73)."""
+    return _fit(_capi.FZ_DFMF, R, None, Theta, obj_types, obj_type2rank, max_iter, init_type, stopping, stopping_system,
+                verbose, compute_err, callback, random_state, engine_kwargs)
+
+
+def dfmc(R, M, Theta, obj_types, obj_type2rank, max_iter=10, init_type="random_vcol", stopping=None, stopping_system=None,
+         verbose=0, compute_err=False, callback=None, random_state=None, n_jobs=1, **engine_kwargs):
+    """Data fusion by matrix completion: as dfmf, with the entries flagged in M re-imputed from the
+    current model every iteration (_dfmc.py:287-292, 319-325).  The caller's R is never modified."""
+    return _fit(_capi.FZ_DFMC, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopping, stopping_system,
+                verbose, compute_err, callback, random_state, engine_kwargs)
+
+
+def transform(R_ij, Theta_i, target_obj_type, obj_type2rank, G, S, max_iter=10, init_type="random_c", stopping=None,
+              stopping_system=None, verbose=0, compute_err=False, callback=None, random_state=None, **engine_kwargs):
+    """Project new objects of ``target_obj_type`` into a fitted latent space: only the target factor
+    is updated, the other factors G and all backbones S stay frozen (_dfmf.py:330-458).  Types are
+    matched by identity, one backbone per type pair, as upstream."""
+    _configure_logging(verbose)
+    if not isinstance(random_state, np.random.RandomState):
+        random_state = np.random.RandomState(random_state)
+    opts = resolve(**engine_kwargs)
+    tgt = target_obj_type
+    n_targets = [mats[0].shape[0 if tgt == ti else 1] for (ti, tj), mats in R_ij.items()]
+    if len(set(n_targets)) > 1:
+        log.critical("Target object type: %s size mismatch" % tgt)
+    n_new = n_targets[0]
+    first = {key: _host_view(mats[0]) for key, mats in R_ij.items()} if init_type != "random" else {}
+    G_i = initialize([tgt], {tgt: n_new}, obj_type2rank, first, init_type, random_state)[tgt, tgt]
+    if max_iter <= 0:
+        return G_i
+
+    prob = _Problem(opts)
+    try:
+        involved = []
+        for (ti, tj), mats in R_ij.items():
+            for t in (ti, tj):
+                if not any(t is u for u in involved):
+                    involved.append(t)
+        sizes = {}
+        for t in involved:
+            sizes[id(t)] = n_new if t is tgt else G[t, t].shape[0]
+        for t in involved:
+            prob.type_id[id(t)] = prob.engine.add_type(sizes[id(t)], int(obj_type2rank[t]))
+        storage = opts.get("storage")
+        rel_of = []
+        for (ti, tj), mats in R_ij.items():
+            for l, mat in enumerate(mats):
+                if not (ti is tgt or tj is tgt):
+                    continue
+                rid = prob.engine.add_relation(prob.type_id[id(ti)], prob.type_id[id(tj)], mat, storage=storage,
+                                               borrow=prob._can_borrow(mat, storage, None))
+                rel_of.append((rid, (ti, tj), l))
+        for key, mats in Theta_i.items():
+            for mat in mats:
+                prob.engine.add_relation(prob.type_id[id(tgt)], prob.type_id[id(tgt)], mat, storage=None)
+        for t in involved:
+            prob.engine.set_factor(prob.type_id[id(t)], G_i if t is tgt else G[t, t])
+        prob.engine.finalize()
+        for rid, key, l in rel_of:
+            prob.engine.set_backbone(rid, S[key][l])
+        prob.engine.transform_prepare(prob.type_id[id(tgt)])
+        if callback is None:
+            prob.engine.transform_iterate(max_iter)
+        else:
+            for it in range(max_iter):
+                prob.engine.transform_iterate(1)
+                callback(prob.engine.get_factor(prob.type_id[id(tgt)]), it)
+        return prob.engine.get_factor(prob.type_id[id(tgt)])
+    finally:
+        prob.close()
