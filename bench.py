@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""DFMF iterations/sec on the synthetic 5-type / 10-relation graph (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the CPU arm (oracle port of the reference, rank 0 only)
+
+A step = one multiplicative-update iteration over the whole graph.  Workload: types 0..4, one relation per
+pair i<j, n objects per type, rank 64, relations stored in bf16 and generated on the device by the engine's
+counter-based generator (identical numbers for every sharding).  The same fixed graph is used at every N
+(strong scaling): type rows are sharded over the ranks, one process per GPU, NCCL for the three exchanges.
+Default n = 81920: the largest power-of-two-ish size whose 10 relations (134 GB) fit one 180 GB B200;
+BASELINE configs[3]'s n=100k (200 GB) needs >= 2 GPUs and can be requested with --n 100000 --gpus >= 2.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "scikit-fusion_b200"))
+
+N_TYPES, RANK, SEED0 = 5, 64, 1000
+PAIRS = [(i, j) for i in range(N_TYPES) for j in range(N_TYPES) if i < j]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=0, help="objects per type (0 = 81920, shrunk if HBM is short)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--split-terms", type=int, default=2)
+    ap.add_argument("--cpu-n", type=int, default=4096, help="objects per type of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(n_workload, n_sample, steps, warmup):
+    """Oracle (float64 numpy port of the reference, reference evaluation order, all host BLAS threads) on a
+    bounded sample of the workload: same graph shape at n_sample objects per type.  The per-iteration time
+    scales as n^2 (three n x n x 64 GEMMs per relation), so it/s at the workload size is extrapolated."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fusion_oracle as oracle
+    types, ranks, R = oracle.hashed_graph(n_sample, N_TYPES, RANK, SEED0, "bfloat16")
+    stamps = []
+    oracle.dfmf(R, {}, types, ranks, max_iter=warmup + steps, init_type="random", random_state=np.random.RandomState(0),
+                callback=lambda G, S, it: stamps.append(time.perf_counter()))
+    per_it = np.diff(stamps)[max(0, warmup - 1):]
+    t_sample = float(np.median(per_it))
+    t_workload = t_sample * (float(n_workload) / n_sample) ** 2
+    return {"t_sample_s": t_sample, "value": 1.0 / t_workload, "cores": os.cpu_count(),
+            "sample": "oracle dfmf, same 5-type/10-relation graph at n=%d per type (float64, %d timed iterations, median "
+                      "%.3f s/it), extrapolated to n=%d by (n/n_sample)^2" % (n_sample, len(per_it), t_sample, n_workload)}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from skfusion import _capi
+    from skfusion.fusion import distributed as fzd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.n
+    if n <= 0:
+        n = 81920
+        free_b, _total = torch.cuda.mem_get_info(dev)
+        while 10.0 * n * n * 2 / world + 4e9 > free_b and n > 8192:   # relations + workspaces must fit
+            n -= 8192
+    lo, hi = fzd.local_rows(n, world, rank)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    # ---- the graph, resident in HBM before any timed region
+    R_local = {}
+    for (i, j) in PAIRS:
+        t = torch.empty((hi - lo, n), dtype=torch.bfloat16, device=dev)
+        _capi.fill_uniform(t, SEED0 + 10 * i + j, row0=lo, stream=stream)
+        R_local[i, j] = [t]
+    rs = np.random.RandomState(0)
+    types = list(range(N_TYPES))
+    sizes = {t: n for t in types}
+    ranks = {t: RANK for t in types}
+    G0 = {(t, t): rs.rand(n, RANK).astype(np.float32) for t in types}
+    opts = dict(dtype="float32", storage="bfloat16", split_terms=args.split_terms)
+    eng, tid, rel_ids = fzd.build_sharded_engine(R_local, sizes, ranks, types, G0, world, rank, local, opts)
+    shard = fzd.CudaShard(eng, local, len(PAIRS), N_TYPES)
+    shard.world, shard.rank = world, rank
+
+    class Solo(object):
+        world, rank = 1, 0
+    coll = fzd.Collectives(dist) if world > 1 else Solo()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    fzd.run_iterations(shard, coll, args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    eng.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    fzd.run_iterations(shard, coll, args.steps)
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    elapsed_ms = e0.elapsed_time(e1)
+    n_prof, prof_ms, prof_bytes = eng.profile_read()
+    eng.profile(False)
+    launches = eng.launches - launches0
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+        ll = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(ll)
+        launches = int(ll.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = 1000.0 / ms_per_step
+
+    # ---- roofline of the dominant kernel (umma_skinny): HBM-bound.  Algorithmic bytes of the
+    # pair of products of one relation = ONE pass over its bf16 matrix; this round runs them as two launches,
+    # so each launch is credited with half of the bytes it streams.
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    alg_bytes_per_launch = 0.5 * prof_bytes / max(1, n_prof)
+    avg_ms = prof_ms / max(1, n_prof)
+    achieved = alg_bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "umma_skinny_kernel<128,*> (tcgen05/TMA streamed skinny product)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src, "launches_timed": n_prof,
+                "avg_launch_ms": round(avg_ms, 4), "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "streamed_bytes_per_launch": prof_bytes / max(1, n_prof),
+                "kernel_share_of_step": round(prof_ms / max(1e-9, elapsed_ms if world == 1 else prof_ms / 1.0), 4) if world == 1 else None}
+
+    # ---- e2e: the same fit through the C ABI with HOST buffers (pinned), H2D of the relations and D2H of the
+    # factors / backbones inside the timed region.
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_leg(args, torch, dist, fzd, _capi, R_local, G0, types, sizes, ranks, world, rank, local, dev, opts, n, lo, hi)
+
+    out = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            c = cpu_arm(n, args.cpu_n, 5, 1)
+            cpu = {"value": c["value"], "unit": "it/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
+        out = {
+            "metric": "DFMF iterations/sec on the synthetic 5-type 10-relation graph", "value": round(value, 4), "unit": "it/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "5 object types x n=%d objects, 10 relations (all pairs i<j) n x n stored bf16, rank 64, "
+                                   "init 'random', factors as %d-term bf16 split with fp32 accumulation, fp64 k x k chain; "
+                                   "type rows sharded over %d GPU(s)" % (n, args.split_terms, world),
+                       "n_per_type": n, "rank": RANK, "relations": len(PAIRS), "split_terms": args.split_terms,
+                       "relation_bytes_total": 10 * n * n * 2,
+                       "cache": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (10.0 * n * (hi - lo) * 2 / 1e9)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": sampler.summary(),
+        }
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def e2e_leg(args, torch, dist, fzd, _capi, R_dev, G0, types, sizes, ranks, world, rank, local, dev, opts, n, lo, hi):
+    """K iterations through build_sharded_engine + run_iterations with HOST inputs: relation row blocks in
+    pinned host memory (bf16), factors as host float32; outputs read back to host numpy."""
+    import psutil
+    need = 10.0 * (hi - lo) * n * 2
+    avail = psutil.virtual_memory().available
+    note = None
+    if need * 1.15 > avail / max(1, world if world > 1 else 1):
+        return {"value": None, "unit": "it/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                "note": "host RAM too small to stage the relations (%.0f GB needed, %.0f GB available)" % (need / 1e9, avail / 1e9)}
+    # stage: device -> pinned host (outside the timed region), then drop the device copies
+    host = {}
+    for key, mats in R_dev.items():
+        h = torch.empty(mats[0].shape, dtype=torch.bfloat16, pin_memory=True)
+        h.copy_(mats[0])
+        host[key] = [h]
+    torch.cuda.synchronize(dev)
+    for key in list(R_dev.keys()):
+        R_dev[key] = None
+    R_dev.clear()
+    torch.cuda.empty_cache()
+
+    class Solo(object):
+        world, rank = 1, 0
+    coll = fzd.Collectives(dist) if world > 1 else Solo()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    eng, tid, rel_ids = fzd.build_sharded_engine(host, sizes, ranks, types, G0, world, rank, local, opts)
+    shard = fzd.CudaShard(eng, local, len(rel_ids), len(types))
+    shard.world, shard.rank = world, rank
+    fzd.run_iterations(shard, coll, args.steps)
+    G = {t: eng.get_factor(tid[t]) for t in types}
+    S = {key: [eng.get_backbone(i) for i in ids] for key, ids in rel_ids.items()}
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    eng.close()
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    h2d = need + sum(g.nbytes for g in G0.values())
+    d2h = sum(g.nbytes for g in G.values()) + sum(s.nbytes for v in S.values() for s in v)
+    return {"value": round(args.steps / dt, 4), "unit": "it/s", "seconds_total": round(dt, 3),
+            "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
+            "note": "one fit of %d iterations through the C ABI from pinned host buffers: upload of the relation row blocks "
+                    "(once per fit) + iterations + download of all factors and backbones, per rank" % args.steps}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return
+        n = args.n if args.n > 0 else 81920
+        c = cpu_arm(n, args.cpu_n, args.steps, args.warmup)
+        print(json.dumps({
+            "impl": "reference", "metric": "DFMF iterations/sec on the synthetic 5-type 10-relation graph",
+            "value": c["value"], "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / c["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "5 object types x n=%d objects, 10 relations, rank 64 (CPU arm measured on a bounded sample)" % n,
+                       "n_per_type": n, "rank": RANK, "relations": len(PAIRS)},
+            "cpu_baseline": {"value": c["value"], "unit": "it/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]},
+            "e2e": {"value": c["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+    gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,6 +106,19 @@ int fz_objective(fz_engine* e, double* per_relation, double* total, void* stream
 /* completed relation G_i S_ij G_j^T (base.py:119-146) into a caller buffer */
 int fz_complete(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int mem, void* stream);
 
+/* ---- measurement ----------------------------------------------------------------------------- */
+/* fz_profile(e, 1) brackets every streamed tensor-core product with CUDA events on its launch stream;
+ * fz_profile_read returns how many launches were timed, the sum of their durations and the relation
+ * bytes they streamed (rows x cols x 2 per launch).  Used by bench.py's roofline leg. */
+int fz_profile(fz_engine* e, int enable);
+int fz_profile_read(fz_engine* e, int64_t* launches, double* total_ms, double* streamed_bytes);
+
+/* ---- synthetic workloads ----------------------------------------------------- */
+/* Fill a rows x cols device matrix (leading dimension ld) with the counter-based uniform [0,1) values
+ * value(r, c) = splitmix64(seed, (row0 + r) * cols + c) >> 40 / 2^24, rounded to `dtype`.  The same
+ * numbers come out of oracle/fusion_oracle.py:hashed_uniform, on any row sharding. */
+int fz_fill_uniform(void* dst, int dtype, int64_t ld, int64_t rows, int64_t cols, int64_t row0, uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

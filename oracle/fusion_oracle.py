@@ -355,6 +355,26 @@ def synthetic_graph(n, n_types=5, rank=64, seed0=1000, storage="float64"):
     return types, ranks, R
 
 
+def hashed_uniform(seed, rows, cols, row0=0):
+    """numpy twin of the engine's fz_fill_uniform (csrc/fz_kernels.cuh:hashed_uniform): float64 array of
+    rows x cols values k / 2^24, element (r, c) a pure function of (seed, (row0 + r) * cols + c)."""
+    idx = (np.arange(row0, row0 + rows, dtype=np.uint64)[:, None] * np.uint64(cols) + np.arange(cols, dtype=np.uint64)[None, :])
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + idx
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(40)).astype(np.float64) / 16777216.0
+
+
+def hashed_graph(n, n_types=5, rank=64, seed0=1000, storage="bfloat16"):
+    """The benchmark graph with counter-based entries: R_ij = hashed_uniform(seed0 + 10 i + j) for i < j."""
+    types = list(range(n_types))
+    R = {(i, j): [round_to_storage(hashed_uniform(seed0 + 10 * i + j, n, n), storage)]
+         for i in types for j in types if i < j}
+    return types, {t: rank for t in types}, R
+
+
 def round_to_storage(a, storage):
     a = np.asarray(a, dtype=np.float64)
     if storage == "float64":

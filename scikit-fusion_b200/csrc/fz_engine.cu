@@ -86,9 +86,32 @@ static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) 
 
 class EngineBase {
  public:
-  virtual ~EngineBase() {}
+  virtual ~EngineBase() {
+    for (auto& pr : prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  }
   std::string err;
   int64_t launches = 0;
+  // optional per-launch timing of the streamed tensor-core products (bench.py's roofline leg)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  double prof_bytes = 0.0;     // relation bytes streamed by the timed launches (rows x cols x 2 each)
+  void prof_begin(cudaStream_t st) {
+    if (!profile) return;
+    if (prof_used == prof_events.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      prof_events.push_back({a, b});
+    }
+    cudaEventRecord(prof_events[prof_used].first, st);
+  }
+  void prof_end(cudaStream_t st, double bytes) {
+    if (!profile) return;
+    cudaEventRecord(prof_events[prof_used].second, st);
+    ++prof_used;
+    prof_bytes += bytes;
+  }
   virtual int compute_dtype() const = 0;
   virtual void set_shard(int world, int rank) = 0;
   virtual int add_type(int64_t n, int k) = 0;
@@ -949,9 +972,11 @@ void Engine<float>::umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g
   if (p.atomic) CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st));
   const CUtensorMap& tx = trans ? r.tmXT : r.tmX;
   const int N = terms_ * kKp;
+  prof_begin(st);
   if (N == 64) { if (trans) umma_launch<64, true>(tx, tg, p, ksplit, st); else umma_launch<64, false>(tx, tg, p, ksplit, st); }
   else if (N == 128) { if (trans) umma_launch<128, true>(tx, tg, p, ksplit, st); else umma_launch<128, false>(tx, tg, p, ksplit, st); }
   else { if (trans) umma_launch<192, true>(tx, tg, p, ksplit, st); else umma_launch<192, false>(tx, tg, p, ksplit, st); }
+  prof_end(st, 2.0 * (double)M * (double)K);
 }
 template <>
 void Engine<double>::umma(RelRec&, bool, const CUtensorMap&, int64_t, double*, int64_t, int, int, int, cudaStream_t) {
@@ -1085,6 +1110,41 @@ int fz_objective(fz_engine* e, double* per_relation, double* total, void* stream
 }
 int fz_complete(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int mem, void* stream) {
   FZ_GUARD(e, e->impl->complete(rel, dst, ld, dst_dtype, mem, (cudaStream_t)stream))
+}
+
+int fz_profile(fz_engine* e, int enable) {
+  if (!e || !e->impl) return FZ_ERR_INVALID;
+  e->impl->profile = enable != 0;
+  e->impl->prof_used = 0;
+  e->impl->prof_bytes = 0.0;
+  return FZ_OK;
+}
+
+int fz_profile_read(fz_engine* e, int64_t* launches, double* total_ms, double* streamed_bytes) {
+  if (!e || !e->impl) return FZ_ERR_INVALID;
+  double ms = 0.0;
+  for (size_t i = 0; i < e->impl->prof_used; ++i) {
+    if (cudaEventSynchronize(e->impl->prof_events[i].second) != cudaSuccess) return FZ_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e->impl->prof_events[i].first, e->impl->prof_events[i].second) != cudaSuccess) return FZ_ERR_CUDA;
+    ms += t;
+  }
+  if (launches) *launches = (int64_t)e->impl->prof_used;
+  if (total_ms) *total_ms = ms;
+  if (streamed_bytes) *streamed_bytes = e->impl->prof_bytes;
+  return FZ_OK;
+}
+
+int fz_fill_uniform(void* dst, int dtype, int64_t ld, int64_t rows, int64_t cols, int64_t row0, uint64_t seed, void* stream) {
+  if (!dst || rows < 0 || cols < 0 || ld < cols) return FZ_ERR_INVALID;
+  if (rows * cols == 0) return FZ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = fz::nblk(rows * cols, 256);
+  if (dtype == FZ_BF16) fz::fill_hashed_uniform<__nv_bfloat16><<<g, 256, 0, st>>>((__nv_bfloat16*)dst, ld, rows, cols, row0, seed);
+  else if (dtype == FZ_F32) fz::fill_hashed_uniform<float><<<g, 256, 0, st>>>((float*)dst, ld, rows, cols, row0, seed);
+  else if (dtype == FZ_F64) fz::fill_hashed_uniform<double><<<g, 256, 0, st>>>((double*)dst, ld, rows, cols, row0, seed);
+  else return FZ_ERR_INVALID;
+  return cudaGetLastError() == cudaSuccess ? FZ_OK : FZ_ERR_CUDA;
 }
 
 }  // extern "C"

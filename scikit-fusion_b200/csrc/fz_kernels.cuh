@@ -488,6 +488,28 @@ __global__ void accum_sign_split(const T* __restrict__ C, T* __restrict__ num, T
   den[i] += n;
 }
 
+// Counter-based synthetic relation entries: value(r, c) = top 24 bits of
+// splitmix64(seed * golden + r * n_cols + c) / 2^24, identical on any sharding and reproducible in
+// numpy (oracle/fusion_oracle.py: hashed_uniform).  Written in the relation's storage dtype.
+__device__ __forceinline__ float hashed_uniform(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed * 0x9E3779B97F4A7C15ull + idx;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+template <class OT> __device__ __forceinline__ OT cast_out(float v) { return (OT)v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cast_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <class OT>
+__global__ void fill_hashed_uniform(OT* __restrict__ dst, long long ld, long long rows, long long cols, long long row0,
+                                    unsigned long long seed) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols, c = idx % cols;
+  dst[r * ld + c] = cast_out<OT>(hashed_uniform(seed, (unsigned long long)((row0 + r) * cols + c)));
+}
+
 template <class T>
 __global__ void fill_value(T* p, long long n, T v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -24,6 +24,7 @@ SYMBOLS = [
     "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_finalize", "fz_iterate",
     "fz_phase_products", "fz_phase_update", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
     "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete",
+    "fz_fill_uniform", "fz_profile", "fz_profile_read",
 ]
 
 
@@ -95,6 +96,9 @@ def lib():
         "fz_get_backbone": (i32, [vp, i32, vp, i64, i32, i32, vp]),
         "fz_objective": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]),
         "fz_complete": (i32, [vp, i32, vp, i64, i32, i32, vp]),
+        "fz_fill_uniform": (i32, [vp, i32, i64, i64, i64, i64, ctypes.c_uint64, vp]),
+        "fz_profile": (i32, [vp, i32]),
+        "fz_profile_read": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -119,6 +123,17 @@ def dtype_code(name):
         raise ValueError("unknown dtype %r (float64 | float32 | bfloat16)" % (name,))
 
 
+def fill_uniform(tensor, seed, row0=0, stream=0):
+    """Fill a 2-D torch CUDA tensor with the engine's counter-based uniform values (see fz_fill_uniform)."""
+    if not _is_torch_cuda(tensor) or tensor.dim() != 2 or tensor.stride(1) != 1:
+        raise ValueError("fill_uniform needs a 2-D torch CUDA tensor with unit inner stride")
+    rc = lib().fz_fill_uniform(ctypes.c_void_p(tensor.data_ptr()), dtype_code(str(tensor.dtype)), int(tensor.stride(0)),
+                               int(tensor.shape[0]), int(tensor.shape[1]), int(row0), int(seed), ctypes.c_void_p(stream))
+    if rc != 0:
+        raise EngineError("fz_fill_uniform failed (%d)" % rc)
+    return tensor
+
+
 def _is_torch_cuda(x):
     return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and bool(x.is_cuda)
 
@@ -132,6 +147,12 @@ def _describe(x, allow_mask=False):
         if str(x.dtype) == "torch.bool":
             code = FZ_U8
         return x, ctypes.c_void_p(x.data_ptr()), int(x.stride(0)), code, FZ_DEVICE
+    if hasattr(x, "data_ptr") and hasattr(x, "is_cuda"):      # torch CPU tensor (e.g. pinned bf16 host buffer)
+        if x.dim() != 2 or x.stride(1) != 1:
+            raise ValueError("host tensors must be 2-D with unit inner stride")
+        name = str(x.dtype)
+        code = FZ_U8 if name in ("torch.uint8", "torch.bool") else dtype_code(name)
+        return x, ctypes.c_void_p(x.data_ptr()), int(x.stride(0)), code, FZ_HOST
     a = np.asarray(x)
     if a.ndim != 2:
         raise ValueError("expected a 2-D matrix, got shape %r" % (a.shape,))
@@ -270,6 +291,15 @@ class Engine(object):
         out = np.empty((ni, nj), dtype=np.float64)
         self._ck(self._L.fz_complete(self._h, rel, ctypes.c_void_p(out.ctypes.data), nj, FZ_F64, FZ_HOST, ctypes.c_void_p(stream)))
         return out
+
+    def profile(self, enable=True):
+        self._ck(self._L.fz_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(timed tensor-core launches, their summed duration in ms, relation bytes they streamed)"""
+        n, ms, b = ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
+        self._ck(self._L.fz_profile_read(self._h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(b)))
+        return n.value, ms.value, b.value
 
     @property
     def launches(self):
