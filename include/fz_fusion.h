@@ -108,10 +108,12 @@ int fz_complete(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int
 
 /* ---- measurement ----------------------------------------------------------------------------- */
 /* fz_profile(e, 1) brackets every streamed tensor-core product with CUDA events on its launch stream;
- * fz_profile_read returns how many launches were timed, the sum of their durations and the relation
- * bytes they streamed (rows x cols x 2 per launch).  Used by bench.py's roofline leg. */
+ * fz_profile_read returns how many launches were timed, the sum of their durations, the relation bytes
+ * they streamed (rows x cols x 2 per launch) and their ALGORITHMIC bytes: one pass over a relation
+ * yields both of its products, so a single-product launch is credited with half of what it streams and
+ * a fused launch with all of it.  Used by bench.py's roofline leg. */
 int fz_profile(fz_engine* e, int enable);
-int fz_profile_read(fz_engine* e, int64_t* launches, double* total_ms, double* streamed_bytes);
+int fz_profile_read(fz_engine* e, int64_t* launches, double* total_ms, double* streamed_bytes, double* algorithmic_bytes);
 
 /* ---- synthetic workloads ----------------------------------------------------- */
 /* Fill a rows x cols device matrix (leading dimension ld) with the counter-based uniform [0,1) values

@@ -8,6 +8,7 @@
 #include <vector>
 #include <string>
 #include "../umma_skinny.cuh"
+#include "../umma_fused.cuh"
 #include "../tmap.h"
 
 #define CK(x)                                                                          \
@@ -142,6 +143,129 @@ static void bench(int n, int terms, bool trans) {
   cudaFree(dX); cudaFree(dG); cudaFree(dC);
 }
 
+// ---- fused single-pass kernel: A = X Gj, B = X^T Gi from one stream of X
+static int run_fused_case(int rows, int cols, int ka, int kb, int csplit) {
+  const int kp = 64, N = 128;
+  const int ld = (cols + 7) / 8 * 8;
+  std::vector<__nv_bfloat16> hX((size_t)rows * ld), hGj((size_t)cols * N), hGi((size_t)rows * N);
+  std::vector<float> fX((size_t)rows * ld), fGj((size_t)cols * N), fGi((size_t)rows * N);
+  for (size_t i = 0; i < hX.size(); ++i) { hX[i] = __float2bfloat16(frand() - 0.3f); fX[i] = __bfloat162float(hX[i]); }
+  auto fillG = [&](std::vector<__nv_bfloat16>& h, std::vector<float>& f, int n, int k) {
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < N; ++c) {
+        int q = c % kp;
+        float v = (q < k) ? (frand() - 0.5f) * ((c / kp) == 0 ? 1.f : 0.004f) : 0.f;
+        h[(size_t)r * N + c] = __float2bfloat16(v);
+        f[(size_t)r * N + c] = __bfloat162float(h[(size_t)r * N + c]);
+      }
+  };
+  fillG(hGj, fGj, cols, ka);
+  fillG(hGi, fGi, rows, kb);
+  __nv_bfloat16 *dX, *dGj, *dGi; float *dA, *dB;
+  CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dGj, hGj.size() * 2)); CK(cudaMalloc(&dGi, hGi.size() * 2));
+  CK(cudaMalloc(&dA, (size_t)rows * ka * 4)); CK(cudaMalloc(&dB, (size_t)cols * kb * 4));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dGj, hGj.data(), hGj.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dGi, hGi.data(), hGi.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dA, 0, (size_t)rows * ka * 4)); CK(cudaMemset(dB, 0, (size_t)cols * kb * 4));
+  CUtensorMap tr, tgj, tgi; std::string err;
+  bool ok = make_tmap_bf16_2d(&tr, dX, rows, cols, ld, 64, 128, &err) && make_tmap_bf16_2d(&tgj, dGj, cols, N, N, 64, 128, &err) &&
+            make_tmap_bf16_2d(&tgi, dGi, rows, N, N, 64, 128, &err);
+  if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
+  FusedParams p;
+  p.A = dA; p.B = dB; p.lda = ka; p.ldb = kb; p.n_rows = rows; p.n_cols = cols; p.k_a = ka; p.k_b = kb; p.gi_row0 = 0;
+  const int tiles = (cols + 127) / 128;
+  p.tiles_per_split = (tiles + csplit - 1) / csplit;
+  const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.a_atomic = splits > 1;
+  CK(cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes));
+  dim3 grid((rows + 255) / 256, splits);
+  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tgj, tgi, p);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hA((size_t)rows * ka), hB((size_t)cols * kb);
+  CK(cudaMemcpy(hA.data(), dA, hA.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hB.data(), dB, hB.size() * 4, cudaMemcpyDeviceToHost));
+  double ma = 0, ea = 0, mb = 0, eb = 0;
+  for (int m = 0; m < rows; ++m)
+    for (int q = 0; q < ka; ++q) {
+      double s = 0;
+      for (int c = 0; c < cols; ++c) s += (double)fX[(size_t)m * ld + c] * ((double)fGj[(size_t)c * N + q] + fGj[(size_t)c * N + kp + q]);
+      ma = fmax(ma, fabs(s)); ea = fmax(ea, fabs(s - hA[(size_t)m * ka + q]));
+    }
+  for (int c = 0; c < cols; ++c)
+    for (int q = 0; q < kb; ++q) {
+      double s = 0;
+      for (int r = 0; r < rows; ++r) s += (double)fX[(size_t)r * ld + c] * ((double)fGi[(size_t)r * N + q] + fGi[(size_t)r * N + kp + q]);
+      mb = fmax(mb, fabs(s)); eb = fmax(eb, fabs(s - hB[(size_t)c * kb + q]));
+    }
+  const bool good = ea / ma < 2e-5 && eb / mb < 2e-5;
+  printf("fused rows=%d cols=%d ka=%d kb=%d csplit=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb, splits, ea / ma,
+         eb / mb, good ? "OK" : "FAIL");
+  cudaFree(dX); cudaFree(dGj); cudaFree(dGi); cudaFree(dA); cudaFree(dB);
+  return good ? 0 : 1;
+}
+
+static void bench_fused(int n) {
+  const int N = 128, k = 64;
+  size_t elems = (size_t)n * n;
+  __nv_bfloat16 *dX, *dG; float *dA, *dB;
+  CK(cudaMalloc(&dX, elems * 2)); CK(cudaMalloc(&dG, (size_t)n * N * 2));
+  CK(cudaMalloc(&dA, (size_t)n * k * 4)); CK(cudaMalloc(&dB, (size_t)n * k * 4));
+  CK(cudaMemset(dX, 0x3c, elems * 2)); CK(cudaMemset(dG, 0x3c, (size_t)n * N * 2));
+  CUtensorMap tr, tg; std::string err;
+  bool ok = make_tmap_bf16_2d(&tr, dX, n, n, n, 64, 128, &err) && make_tmap_bf16_2d(&tg, dG, n, N, N, 64, 128, &err);
+  if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
+  CK(cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes));
+  for (int csplit : {1, 2, 4, 8}) {
+    FusedParams p;
+    p.A = dA; p.B = dB; p.lda = k; p.ldb = k; p.n_rows = n; p.n_cols = n; p.k_a = k; p.k_b = k; p.gi_row0 = 0;
+    const int tiles = (n + 127) / 128;
+    p.tiles_per_split = (tiles + csplit - 1) / csplit;
+    const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    p.a_atomic = splits > 1;
+    dim3 grid((n + 255) / 256, splits);
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 2; ++w) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg, tg, p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    const int reps = 5;
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg, tg, p);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+    printf("bench FUSED n=%d csplit=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", n, splits, grid.x, grid.y,
+           ms, elems * 2.0 / 1e9 / (ms * 1e-3), 2.0 * 2.0 * elems * N / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(dX); cudaFree(dG); cudaFree(dA); cudaFree(dB);
+}
+
+// v1 kernel on an L2-resident matrix: the SM-side (smem / tensor) throughput limit without HBM in the way
+static void bench_l2_resident() {
+  const int rows = 8192, cols = 4096, N = 128, k = 64;   // 64 MB of bf16: stays in the 126 MB L2
+  __nv_bfloat16 *dX, *dG; float* dC;
+  CK(cudaMalloc(&dX, (size_t)rows * cols * 2)); CK(cudaMalloc(&dG, (size_t)cols * N * 2)); CK(cudaMalloc(&dC, (size_t)rows * k * 4));
+  CK(cudaMemset(dX, 0x3c, (size_t)rows * cols * 2)); CK(cudaMemset(dG, 0x3c, (size_t)cols * N * 2));
+  CUtensorMap tx, tg; std::string err;
+  bool ok = make_tmap_bf16_2d(&tx, dX, rows, cols, cols, 64, 128, &err) && make_tmap_bf16_2d(&tg, dG, cols, N, N, 64, 64, &err);
+  if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
+  SkinnyParams p;
+  p.C = dC; p.ldc = k; p.g_row0 = 0; p.M = rows; p.K = cols; p.k = k; p.kp = 64; p.terms = 2;
+  const int ksplit = 4;
+  p.k_per_split = cols / ksplit; p.atomic = 1;
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int w = 0; w < 3; ++w) dispatch(N, false, tx, tg, p, ksplit, 0);
+  CK(cudaDeviceSynchronize());
+  const int reps = 20;
+  CK(cudaEventRecord(e0));
+  for (int r = 0; r < reps; ++r) dispatch(N, false, tx, tg, p, ksplit, 0);
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+  printf("bench L2-resident (64 MB, v1 kernel N=128, ksplit=4): %.4f ms  %.1f GB/s from L2\n", ms,
+         (double)rows * cols * 2 / 1e9 / (ms * 1e-3));
+  cudaFree(dX); cudaFree(dG); cudaFree(dC);
+}
+
 int main(int argc, char** argv) {
   int nbench = argc > 1 ? atoi(argv[1]) : 32768;
   int fails = 0;
@@ -154,8 +278,16 @@ int main(int argc, char** argv) {
     }
   fails += run_case(2048, 4096, 64, 2, false, 4, true) > 2e-5;
   fails += run_case(4096, 2048, 64, 2, true, 4, true) > 2e-5;
+  fails += run_fused_case(256, 256, 64, 64, 1);
+  fails += run_fused_case(512, 384, 64, 64, 1);
+  fails += run_fused_case(1000, 520, 64, 40, 1);
+  fails += run_fused_case(520, 1000, 50, 64, 3);
+  fails += run_fused_case(130, 77, 7, 12, 1);
+  fails += run_fused_case(2048, 4096, 64, 64, 4);
   printf("correctness: %d failing cases\n", fails);
   if (nbench > 0) {
+    bench_l2_resident();
+    bench_fused(nbench);
     for (int trans = 0; trans < 2; ++trans)
       for (int terms = 1; terms <= 2; ++terms) bench(nbench, terms, trans);
   }

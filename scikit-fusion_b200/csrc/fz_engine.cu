@@ -25,6 +25,7 @@
 #include "fz_chain.cuh"
 #include "fz_kernels.cuh"
 #include "tmap.h"
+#include "umma_fused.cuh"
 #include "umma_skinny.cuh"
 
 namespace fz {
@@ -96,6 +97,8 @@ class EngineBase {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
   double prof_bytes = 0.0;     // relation bytes streamed by the timed launches (rows x cols x 2 each)
+  double prof_alg_bytes = 0.0; // algorithmic share: a launch that yields only one of the two products of a
+                               // relation is credited with half of the bytes it streams (one pass feeds both)
   void prof_begin(cudaStream_t st) {
     if (!profile) return;
     if (prof_used == prof_events.size()) {
@@ -106,11 +109,12 @@ class EngineBase {
     }
     cudaEventRecord(prof_events[prof_used].first, st);
   }
-  void prof_end(cudaStream_t st, double bytes) {
+  void prof_end(cudaStream_t st, double bytes, int products_per_pass = 2) {
     if (!profile) return;
     cudaEventRecord(prof_events[prof_used].second, st);
     ++prof_used;
     prof_bytes += bytes;
+    prof_alg_bytes += bytes / products_per_pass;   // 2: single-product launch (half credit); 1: fused launch
   }
   virtual int compute_dtype() const = 0;
   virtual void set_shard(int world, int rank) = 0;
@@ -224,7 +228,8 @@ class Engine : public EngineBase {
     bool has_factor = false;
     bool need_gs = false;
     DevBuf Gs;               // bf16 [n_pad][terms*kKp]
-    CUtensorMap tmG;
+    CUtensorMap tmG;         // box {64 cols, 64 rows}   (two-pass kernels)
+    CUtensorMap tmG128;      // box {64 cols, 128 rows}  (fused kernel)
     DevBuf gram_part;
     int gram_chunks = 0, gram_rows_per_chunk = 0;
     double* gram_raw = nullptr;  // inside `small`
@@ -256,6 +261,8 @@ class Engine : public EngineBase {
   int device_;
   int world_ = 1, rank_ = 0;
   int terms_ = 2;
+  bool fused_ = true;       // single-pass A/B kernel for bf16 relations (needs terms_ == 2); FZ_NO_FUSED=1 disables
+  int fused_csplit_ = 0;    // column splits of the fused kernel (0 = automatic); FZ_FUSED_CSPLIT overrides
   bool finalized_ = false;
   bool dfmc_started_ = false;
   std::vector<std::unique_ptr<TypeRec>> types_;
@@ -408,7 +415,8 @@ class Engine : public EngineBase {
       if (t.need_gs) {
         t.Gs.alloc((size_t)t.n_pad * terms_ * kKp * 2);
         std::string e;
-        if (!make_tmap_bf16_2d(&t.tmG, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 64, &e))
+        if (!make_tmap_bf16_2d(&t.tmG, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 64, &e) ||
+            !make_tmap_bf16_2d(&t.tmG128, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 128, &e))
           FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
       }
     }
@@ -440,6 +448,9 @@ class Engine : public EngineBase {
       }
     }
     err_acc_.alloc(8);
+    if (const char* nf = getenv("FZ_NO_FUSED")) fused_ = !(nf[0] == '1');
+    if (const char* cs = getenv("FZ_FUSED_CSPLIT")) fused_csplit_ = atoi(cs);
+    if (terms_ != 2) fused_ = false;
     build_job_tables();
     // opt in to the large dynamic shared memory of the tensor-core kernels
     set_umma_attrs();
@@ -479,8 +490,10 @@ class Engine : public EngineBase {
     grams(st);
     for (auto& rp : rels_) {
       if (rp->theta) continue;
-      product_A(*rp, st);
-      product_B(*rp, st);
+      if (!product_AB_fused(*rp, st)) {
+        product_A(*rp, st);
+        product_B(*rp, st);
+      }
       reduce_M(*rp, st);
     }
     theta_products(st);
@@ -716,6 +729,7 @@ class Engine : public EngineBase {
     umma_attr<64, false>(); umma_attr<64, true>();
     umma_attr<128, false>(); umma_attr<128, true>();
     umma_attr<192, false>(); umma_attr<192, true>();
+    cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes);
   }
   // tensor-core product of a bf16 relation with a split factor:  C (M x k) = op(R) * Gs[g_row0 + ., :]
   void umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g_row0, T* C, int64_t ldc, int M, int K, int k, cudaStream_t st);
@@ -757,6 +771,9 @@ class Engine : public EngineBase {
     if (r.storage == FZ_BF16) umma(r, true, Ti.tmG, Ti.row0, r.B.template as<T>(), Ti.k, (int)r.cols, (int)r.rows_loc, Ti.k, st);
     else gemm_t((const T*)r.data, r.ld, cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.B.template as<T>(), Ti.k, (int)r.cols, Ti.k, (int)r.rows_loc, st);
   }
+  // A and B from ONE stream of a bf16 relation (umma_fused.cuh).  Returns false when not applicable.
+  bool product_AB_fused(RelRec& r, cudaStream_t st);
+
   void reduce_M(RelRec& r, cudaStream_t st) {    // M = G_i[local]^T A    (fp64 accumulate)
     TypeRec& Ti = *types_[r.ti];
     TypeRec& Tj = *types_[r.tj];
@@ -979,6 +996,44 @@ void Engine<float>::umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g
   prof_end(st, 2.0 * (double)M * (double)K);
 }
 template <>
+bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
+  if (!fused_ || r.storage != FZ_BF16 || r.rows_loc <= 0) return false;
+  TypeRec& Ti = *types_[r.ti];
+  TypeRec& Tj = *types_[r.tj];
+  FusedParams p;
+  p.A = r.A.template as<float>();
+  p.B = r.B.template as<float>();
+  p.lda = Tj.k;
+  p.ldb = Ti.k;
+  p.n_rows = (int)r.rows_loc;
+  p.n_cols = (int)r.cols;
+  p.k_a = Tj.k;
+  p.k_b = Ti.k;
+  p.gi_row0 = (int)Ti.row0;
+  const int pairs = (int)((r.rows_loc + 2 * kFuTile - 1) / (2 * kFuTile));
+  const int tiles = (int)((r.cols + kFuTile - 1) / kFuTile);
+  int splits = fused_csplit_;
+  if (splits <= 0) {
+    splits = (148 * 6 + pairs - 1) / pairs;            // ~6 CTAs per SM in total
+    splits = std::min(splits, std::max(1, tiles / 8)); // but keep >= 8 column tiles per CTA
+  }
+  splits = std::max(1, std::min(splits, tiles));
+  p.tiles_per_split = (tiles + splits - 1) / splits;
+  splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.a_atomic = splits > 1 ? 1 : 0;
+  CUDA_OK(cudaMemsetAsync(r.B.p, 0, r.B.bytes, st));
+  if (p.a_atomic) CUDA_OK(cudaMemsetAsync(r.A.p, 0, (size_t)r.rows_loc * Tj.k * sizeof(float), st));
+  dim3 grid(pairs, splits);
+  prof_begin(st);
+  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(r.tmX, Tj.tmG128, Ti.tmG128, p);
+  ++launches;
+  prof_end(st, 2.0 * (double)r.rows_loc * (double)r.cols, /*passes=*/1);
+  return true;
+}
+template <>
+bool Engine<double>::product_AB_fused(RelRec&, cudaStream_t) { return false; }
+
+template <>
 void Engine<double>::umma(RelRec&, bool, const CUtensorMap&, int64_t, double*, int64_t, int, int, int, cudaStream_t) {
   FZ_THROW(FZ_ERR_UNSUPPORTED, "tensor-core path needs the fp32 engine");
 }
@@ -1117,10 +1172,11 @@ int fz_profile(fz_engine* e, int enable) {
   e->impl->profile = enable != 0;
   e->impl->prof_used = 0;
   e->impl->prof_bytes = 0.0;
+  e->impl->prof_alg_bytes = 0.0;
   return FZ_OK;
 }
 
-int fz_profile_read(fz_engine* e, int64_t* launches, double* total_ms, double* streamed_bytes) {
+int fz_profile_read(fz_engine* e, int64_t* launches, double* total_ms, double* streamed_bytes, double* algorithmic_bytes) {
   if (!e || !e->impl) return FZ_ERR_INVALID;
   double ms = 0.0;
   for (size_t i = 0; i < e->impl->prof_used; ++i) {
@@ -1132,6 +1188,7 @@ int fz_profile_read(fz_engine* e, int64_t* launches, double* total_ms, double* s
   if (launches) *launches = (int64_t)e->impl->prof_used;
   if (total_ms) *total_ms = ms;
   if (streamed_bytes) *streamed_bytes = e->impl->prof_bytes;
+  if (algorithmic_bytes) *algorithmic_bytes = e->impl->prof_alg_bytes;
   return FZ_OK;
 }
 

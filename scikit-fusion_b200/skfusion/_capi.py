@@ -98,7 +98,8 @@ def lib():
         "fz_complete": (i32, [vp, i32, vp, i64, i32, i32, vp]),
         "fz_fill_uniform": (i32, [vp, i32, i64, i64, i64, i64, ctypes.c_uint64, vp]),
         "fz_profile": (i32, [vp, i32]),
-        "fz_profile_read": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+        "fz_profile_read": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                  ctypes.POINTER(ctypes.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -296,10 +297,10 @@ class Engine(object):
         self._ck(self._L.fz_profile(self._h, 1 if enable else 0))
 
     def profile_read(self):
-        """(timed tensor-core launches, their summed duration in ms, relation bytes they streamed)"""
-        n, ms, b = ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
-        self._ck(self._L.fz_profile_read(self._h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(b)))
-        return n.value, ms.value, b.value
+        """(timed tensor-core launches, summed duration in ms, relation bytes streamed, algorithmic bytes)"""
+        n, ms, b, a = ctypes.c_int64(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        self._ck(self._L.fz_profile_read(self._h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(b), ctypes.byref(a)))
+        return n.value, ms.value, b.value, a.value
 
     @property
     def launches(self):
