@@ -208,6 +208,8 @@ def gpu_arm(args):
     # ---- e2e: the same fit through the C ABI with HOST buffers (pinned), H2D of the relations and D2H of the
     # factors / backbones inside the timed region.
     e2e = None
+    eng.close()                      # frees the engine's buffers and drops its references to the borrowed relations
+    del shard
     if not args.no_e2e:
         e2e = e2e_leg(args, torch, dist, fzd, _capi, R_local, G0, types, sizes, ranks, world, rank, local, dev, opts, n, lo, hi)
 
@@ -230,7 +232,6 @@ def gpu_arm(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(),
         }
-    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -258,6 +259,9 @@ def e2e_leg(args, torch, dist, fzd, _capi, R_dev, G0, types, sizes, ranks, world
     for key in list(R_dev.keys()):
         R_dev[key] = None
     R_dev.clear()
+    del mats
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
 
     class Solo(object):
