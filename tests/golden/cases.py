@@ -71,3 +71,20 @@ def transform_cases():
                              Theta={("t3", "t3"): [_sparse_sym_constraint(rs, 9, 0.5, 0.05)]},
                              init_type="random", seed=12, max_iter=60, snapshots=[0, 9, 59])
     return c
+
+
+def dicty_case(path=None):
+    """BASELINE config C2: the dicty graph (Gene 1219 / GO term 116 / Experimental condition 282; ranks
+    50 / 15 / 5 as in datasets/base.py:45-61), rebuilt from the derived fixture dicty_matrices.npz."""
+    import os
+    path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "dicty_matrices.npz")
+    z = np.load(path)
+    shape = tuple(z["ann_shape"])
+    ann = np.unpackbits(z["ann_bits"], axis=1)[:, :shape[1]].astype(np.float64)
+    expr = z["expr"].astype(np.float64)
+    ppi = np.zeros(tuple(z["ppi_shape"]))
+    ppi[z["ppi_rows"], z["ppi_cols"]] = z["ppi_vals"].astype(np.float64)
+    return dict(algo="dfmf", types=["Gene", "GO term", "Experimental condition"],
+                ranks={"Gene": 50, "GO term": 15, "Experimental condition": 5},
+                R={("Gene", "GO term"): [ann], ("Gene", "Experimental condition"): [expr]},
+                Theta={("Gene", "Gene"): [ppi]}, M=None, init_type="random_vcol", seed=0, max_iter=50)

@@ -193,3 +193,30 @@ def test_pinv_chain_on_ill_conditioned_and_singular_grams():
         Go, So = oracle.dfmf(R, {}, ["i", "j"], ranks, max_iter=1, G0={("i", "i"): Gi, ("j", "j"): Gj})
     assert rel_fro(So["i", "j"][0], S) < 1e-6
     assert rel_fro(Go["i", "i"], G1) < 1e-6
+
+
+@pytest.mark.parametrize("algo", ["dfmf", "dfmc"])
+def test_dicty_config_fp32_against_oracle(algo):
+    """BASELINE config C2: the dicty graph, fp32 engine vs the float64 oracle on identical inputs and seed,
+    50 iterations, random_vcol init (near-collinear columns, cond(G^T G) ~ 1e5: the F7 stress case)."""
+    from skfusion.fusion import solver
+    case = cases.dicty_case()
+    kw = dict(obj_types=case["types"], obj_type2rank=case["ranks"], max_iter=case["max_iter"], init_type=case["init_type"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if algo == "dfmf":
+            Go, So = oracle.dfmf(case["R"], case["Theta"], random_state=np.random.RandomState(0), **kw)
+            G, S = solver.dfmf(case["R"], case["Theta"], random_state=np.random.RandomState(0), dtype="float32", **kw)
+        else:
+            M = {key: [None] for key in case["R"]}
+            M["Gene", "GO term"] = [np.random.RandomState(5).rand(1219, 116) > 0.9]
+            Go, So = oracle.dfmc(case["R"], M, case["Theta"], random_state=np.random.RandomState(0), **kw)
+            G, S = solver.dfmc(case["R"], M, case["Theta"], random_state=np.random.RandomState(0), dtype="float32", **kw)
+    for t in case["types"]:
+        err = rel_fro(Go[t, t], G[t, t])
+        assert err < 1e-4, "G[%s] relFro=%.3g" % (t, err)
+    for key in So:
+        err = rel_fro(So[key][0], S[key][0])
+        assert err < 1e-3, "S%s relFro=%.3g" % (key, err)
+    obj_o, obj_g = oracle.objective(case["R"], Go, So)[0], oracle.objective(case["R"], G, S)[0]
+    assert abs(obj_o - obj_g) / obj_o < 1e-5
