@@ -144,7 +144,7 @@ static void bench(int n, int terms, bool trans) {
 }
 
 // ---- fused single-pass kernel: A = X Gj, B = X^T Gi from one stream of X
-static int run_fused_case(int rows, int cols, int ka, int kb, int csplit) {
+static int run_fused_case(int rows, int cols, int ka, int kb, int csplit, int tma_flush = 1) {
   const int kp = 64, N = 128;
   const int ld = (cols + 7) / 8 * 8;
   std::vector<__nv_bfloat16> hX((size_t)rows * ld), hGj((size_t)cols * N), hGi((size_t)rows * N);
@@ -168,19 +168,22 @@ static int run_fused_case(int rows, int cols, int ka, int kb, int csplit) {
   CK(cudaMemcpy(dGj, hGj.data(), hGj.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dGi, hGi.data(), hGi.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dA, 0, (size_t)rows * ka * 4)); CK(cudaMemset(dB, 0, (size_t)cols * kb * 4));
-  CUtensorMap tr, tgj, tgi; std::string err;
-  bool ok = make_tmap_bf16_2d(&tr, dX, rows, cols, ld, 64, 128, &err) && make_tmap_bf16_2d(&tgj, dGj, cols, N, N, 64, 128, &err) &&
+  CUtensorMap tr, tgj, tgi, tb; std::string err;
+  if (kb % 4 != 0 || kb < 32) tma_flush = 0;
+  bool ok = make_tmap_bf16_2d(&tr, dX, rows, cols, ld, 64, 128, &err) && make_tmap_bf16_2d(&tgj, dGj, cols, N, N, 64, 64, &err) &&
             make_tmap_bf16_2d(&tgi, dGi, rows, N, N, 64, 128, &err);
+  if (ok && tma_flush) ok = make_tmap_f32_2d(&tb, dB, cols, kb, kb, 32, 32, &err);
+  if (!tma_flush) tb = tr;
   if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
   FusedParams p;
-  p.A = dA; p.B = dB; p.lda = ka; p.ldb = kb; p.n_rows = rows; p.n_cols = cols; p.k_a = ka; p.k_b = kb; p.gi_row0 = 0;
+  p.A = dA; p.B = dB; p.lda = ka; p.ldb = kb; p.n_rows = rows; p.n_cols = cols; p.k_a = ka; p.k_b = kb; p.gi_row0 = 0; p.probe_skip_flush = 0; p.tma_flush = tma_flush;
   const int tiles = (cols + 127) / 128;
   p.tiles_per_split = (tiles + csplit - 1) / csplit;
   const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.a_atomic = splits > 1;
   CK(cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes));
   dim3 grid((rows + 255) / 256, splits);
-  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tgj, tgi, p);
+  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tgj, tgi, tb, p);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> hA((size_t)rows * ka), hB((size_t)cols * kb);
@@ -200,41 +203,43 @@ static int run_fused_case(int rows, int cols, int ka, int kb, int csplit) {
       mb = fmax(mb, fabs(s)); eb = fmax(eb, fabs(s - hB[(size_t)c * kb + q]));
     }
   const bool good = ea / ma < 2e-5 && eb / mb < 2e-5;
-  printf("fused rows=%d cols=%d ka=%d kb=%d csplit=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb, splits, ea / ma,
-         eb / mb, good ? "OK" : "FAIL");
+  printf("fused rows=%d cols=%d ka=%d kb=%d csplit=%d flush=%s : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb, splits,
+         tma_flush ? "tma" : "red", ea / ma, eb / mb, good ? "OK" : "FAIL");
   cudaFree(dX); cudaFree(dGj); cudaFree(dGi); cudaFree(dA); cudaFree(dB);
   return good ? 0 : 1;
 }
 
-static void bench_fused(int n) {
+static void bench_fused(int n, int skip_flush) {
   const int N = 128, k = 64;
   size_t elems = (size_t)n * n;
   __nv_bfloat16 *dX, *dG; float *dA, *dB;
   CK(cudaMalloc(&dX, elems * 2)); CK(cudaMalloc(&dG, (size_t)n * N * 2));
   CK(cudaMalloc(&dA, (size_t)n * k * 4)); CK(cudaMalloc(&dB, (size_t)n * k * 4));
   CK(cudaMemset(dX, 0x3c, elems * 2)); CK(cudaMemset(dG, 0x3c, (size_t)n * N * 2));
-  CUtensorMap tr, tg; std::string err;
-  bool ok = make_tmap_bf16_2d(&tr, dX, n, n, n, 64, 128, &err) && make_tmap_bf16_2d(&tg, dG, n, N, N, 64, 128, &err);
+  CUtensorMap tr, tg, tg64, tb; std::string err;
+  bool ok = make_tmap_bf16_2d(&tr, dX, n, n, n, 64, 128, &err) && make_tmap_bf16_2d(&tg, dG, n, N, N, 64, 128, &err) &&
+            make_tmap_bf16_2d(&tg64, dG, n, N, N, 64, 64, &err) && make_tmap_f32_2d(&tb, dB, n, k, k, 32, 32, &err);
   if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
   CK(cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes));
-  for (int csplit : {1, 2, 4, 8}) {
+  for (int csplit : {1}) {
     FusedParams p;
     p.A = dA; p.B = dB; p.lda = k; p.ldb = k; p.n_rows = n; p.n_cols = n; p.k_a = k; p.k_b = k; p.gi_row0 = 0;
+    p.probe_skip_flush = skip_flush & 7; p.tma_flush = (skip_flush & 8) ? 0 : 1;
     const int tiles = (n + 127) / 128;
     p.tiles_per_split = (tiles + csplit - 1) / csplit;
     const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
     p.a_atomic = splits > 1;
     dim3 grid((n + 255) / 256, splits);
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int w = 0; w < 2; ++w) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg, tg, p);
+    for (int w = 0; w < 2; ++w) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, p);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    const int reps = 5;
+    const int reps = 40;
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg, tg, p);
+    for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, p);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
-    printf("bench FUSED n=%d csplit=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", n, splits, grid.x, grid.y,
+    printf("bench FUSED%s n=%d csplit=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", skip_flush == 0 ? " (tma flush)" : skip_flush == 8 ? " (red flush)" : (skip_flush == 1 ? " (probe: no RED)" : (skip_flush == 2 ? " (probe: no B MMA)" : (skip_flush == 4 ? " (probe: no A MMA)" : (skip_flush == 3 ? " (probe: no RED, no B MMA)" : " (probe: TMA only)")))), n, splits, grid.x, grid.y,
            ms, elems * 2.0 / 1e9 / (ms * 1e-3), 2.0 * 2.0 * elems * N / (ms * 1e-3) / 1e12);
   }
   cudaFree(dX); cudaFree(dG); cudaFree(dA); cudaFree(dB);
@@ -284,10 +289,15 @@ int main(int argc, char** argv) {
   fails += run_fused_case(520, 1000, 50, 64, 3);
   fails += run_fused_case(130, 77, 7, 12, 1);
   fails += run_fused_case(2048, 4096, 64, 64, 4);
+  fails += run_fused_case(1000, 520, 64, 40, 1, 0);
+  fails += run_fused_case(2048, 4096, 64, 64, 4, 0);
+  fails += run_fused_case(3000, 2100, 33, 36, 2);
+  fails += run_fused_case(777, 3001, 64, 64, 1);
   printf("correctness: %d failing cases\n", fails);
   if (nbench > 0) {
     bench_l2_resident();
-    bench_fused(nbench);
+    for (int mode : {0, 8, 1, 7}) bench_fused(nbench, mode);
+    return fails ? 1 : 0;
     for (int trans = 0; trans < 2; ++trans)
       for (int terms = 1; terms <= 2; ++terms) bench(nbench, terms, trans);
   }

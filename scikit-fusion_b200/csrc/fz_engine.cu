@@ -255,7 +255,8 @@ class Engine : public EngineBase {
     int m_chunks = 0, m_rows_per_chunk = 0;
     DevBuf S, t2, t5, W1, W4, work;
     bool has_backbone = false;
-    CUtensorMap tmX, tmXT, tmEs;
+    CUtensorMap tmX, tmXT, tmEs, tmB;
+    bool has_tmB = false;
   };
 
   int device_;
@@ -445,6 +446,9 @@ class Engine : public EngineBase {
         bool ok = make_tmap_bf16_2d(&r.tmX, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols, (uint64_t)r.ld, 64, 128, &e) &&
                   make_tmap_bf16_2d(&r.tmXT, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols, (uint64_t)r.ld, 64, 64, &e);
         if (!ok) FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+        // reduce target of the fused kernel's TMA flush (fp32, box 32 x 32, 128B swizzle)
+        if (kDT == FZ_F32 && (Ti.k % 4) == 0 && Ti.k >= 32)
+          r.has_tmB = make_tmap_f32_2d(&r.tmB, r.B.p, (uint64_t)Tj.n_pad, (uint64_t)Ti.k, (uint64_t)Ti.k, 32, 32, &e);
       }
     }
     err_acc_.alloc(8);
@@ -1010,6 +1014,8 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   p.k_a = Tj.k;
   p.k_b = Ti.k;
   p.gi_row0 = (int)Ti.row0;
+  p.probe_skip_flush = 0;
+  p.tma_flush = r.has_tmB ? 1 : 0;
   const int pairs = (int)((r.rows_loc + 2 * kFuTile - 1) / (2 * kFuTile));
   const int tiles = (int)((r.cols + kFuTile - 1) / kFuTile);
   int splits = fused_csplit_;
@@ -1025,7 +1031,7 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   if (p.a_atomic) CUDA_OK(cudaMemsetAsync(r.A.p, 0, (size_t)r.rows_loc * Tj.k * sizeof(float), st));
   dim3 grid(pairs, splits);
   prof_begin(st);
-  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(r.tmX, Tj.tmG128, Ti.tmG128, p);
+  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(r.tmX, Tj.tmG, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX, p);
   ++launches;
   prof_end(st, 2.0 * (double)r.rows_loc * (double)r.cols, /*passes=*/1);
   return true;
