@@ -15,9 +15,36 @@ namespace fz {
 
 constexpr int kChainThreads = 512;
 
+constexpr int kChainSmemDim = 64;                                         // operands up to 64 x 64 are staged in smem
+constexpr int kChainSmemBytes = 2 * kChainSmemDim * (kChainSmemDim + 1) * 8;   // two padded operand tiles
+
 // C[m x n] = op(A) * op(B), all row-major fp64; executed by the whole block; caller syncs afterwards.
+// When both operands fit 64 x 64 they are first copied (already transposed as needed) into shared memory `stage`
+// (kChainSmemBytes), which turns ~2*kk dependent global loads per output into conflict-free shared loads.
 __device__ __forceinline__ void block_mm(double* C, int ldc, const double* A, int lda, bool ta, const double* B, int ldb,
-                                         bool tb, int m, int n, int kk) {
+                                         bool tb, int m, int n, int kk, double* stage = nullptr) {
+  if (stage != nullptr && m <= kChainSmemDim && n <= kChainSmemDim && kk <= kChainSmemDim) {
+    double(*sA)[kChainSmemDim + 1] = reinterpret_cast<double(*)[kChainSmemDim + 1]>(stage);                          // [m][kk]
+    double(*sB)[kChainSmemDim + 1] = reinterpret_cast<double(*)[kChainSmemDim + 1]>(stage + kChainSmemDim * (kChainSmemDim + 1));  // [kk][n]
+    __syncthreads();   // previous users of the staging area are done
+    for (int o = threadIdx.x; o < m * kk; o += blockDim.x) {
+      const int i = o / kk, c = o % kk;
+      sA[i][c] = ta ? A[(long long)c * lda + i] : A[(long long)i * lda + c];
+    }
+    for (int o = threadIdx.x; o < kk * n; o += blockDim.x) {
+      const int c = o / n, j = o % n;
+      sB[c][j] = tb ? B[(long long)j * ldb + c] : B[(long long)c * ldb + j];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < m * n; o += blockDim.x) {
+      const int i = o / n, j = o % n;
+      double s = 0.0;
+#pragma unroll 8
+      for (int c = 0; c < kk; ++c) s += sA[i][c] * sB[c][j];
+      C[(long long)i * ldc + j] = s;
+    }
+    return;
+  }
   for (int o = threadIdx.x; o < m * n; o += blockDim.x) {
     const int i = o / n, j = o % n;
     double s = 0.0;
@@ -44,8 +71,10 @@ pinv_spd(const PinvJob* __restrict__ jobs) {
   const PinvJob job = jobs[blockIdx.x];
   const int k = job.k;
   const int tid = threadIdx.x, nth = blockDim.x;
-  double* L = job.work;                 // k x k
-  double* X = job.work + (long long)k * k;      // k x k
+  extern __shared__ double chain_stage[];
+  const bool in_smem = (k <= kChainSmemDim);    // small ranks: factor and its inverse live in shared memory
+  double* L = in_smem ? chain_stage : job.work;                              // k x k
+  double* X = in_smem ? chain_stage + k * k : job.work + (long long)k * k;  // k x k
   double* V = job.work + 2ll * k * k;           // k x k (Jacobi)
   __shared__ double s_maxdiag;
   __shared__ int s_fail;
@@ -115,7 +144,8 @@ pinv_spd(const PinvJob* __restrict__ jobs) {
   // ---------------------------------------------------------------- one-sided Jacobi on the rows of W = A
   // (A symmetric: rows == columns).  After convergence row p of W is (A v_p)^T with v_p = row p of V,
   // sigma_p = |row p|, and pinv(A) = sum_{sigma_p > cutoff} v_p (A v_p)^T / sigma_p^2.
-  double* W = L;
+  double* W = job.work;                 // the eigen-solve always runs out of the global workspace
+  X = job.work + (long long)k * k;
   for (int o = tid; o < k * k; o += nth) {
     W[o] = job.gram[o];
     V[o] = (o / k == o % k) ? 1.0 : 0.0;
@@ -229,26 +259,28 @@ backbone_chain(const BackboneJob<T>* __restrict__ jobs) {
   const int km = max(ki, kj);
   double* U = job.work;
   double* Vw = job.work + (long long)km * km;
+  extern __shared__ double chain_stage[];
+  double* stage = (km <= kChainSmemDim) ? chain_stage : nullptr;
   if (job.solve) {
     // Vw = scrub(M) ; U = Vw * P_j ; S = scrub(P_i * U)
     for (int o = tid; o < ki * kj; o += nth) Vw[o] = scrub(job.M_raw[o]);
     __syncthreads();
-    block_mm(U, kj, Vw, kj, false, job.P_j, kj, false, ki, kj, kj);
+    block_mm(U, kj, Vw, kj, false, job.P_j, kj, false, ki, kj, kj, stage);
     __syncthreads();
-    block_mm(job.S, kj, job.P_i, ki, false, U, kj, false, ki, kj, ki);
+    block_mm(job.S, kj, job.P_i, ki, false, U, kj, false, ki, kj, ki, stage);
     __syncthreads();
     for (int o = tid; o < ki * kj; o += nth) job.S[o] = scrub(job.S[o]);
     __syncthreads();
   }
   // t2 = S gram_j S^T
-  block_mm(U, kj, job.S, kj, false, job.gram_j, kj, false, ki, kj, kj);
+  block_mm(U, kj, job.S, kj, false, job.gram_j, kj, false, ki, kj, kj, stage);
   __syncthreads();
-  block_mm(job.t2, ki, U, kj, false, job.S, kj, true, ki, ki, kj);
+  block_mm(job.t2, ki, U, kj, false, job.S, kj, true, ki, ki, kj, stage);
   __syncthreads();
   // t5 = S^T gram_i S
-  block_mm(U, ki, job.S, kj, true, job.gram_i, ki, false, kj, ki, ki);
+  block_mm(U, ki, job.S, kj, true, job.gram_i, ki, false, kj, ki, ki, stage);
   __syncthreads();
-  block_mm(job.t5, kj, U, ki, false, job.S, kj, false, kj, kj, ki);
+  block_mm(job.t5, kj, U, ki, false, job.S, kj, false, kj, kj, ki, stage);
   __syncthreads();
   if (job.scrub) {
     for (int o = tid; o < ki * ki; o += nth) job.t2[o] = scrub(job.t2[o]);

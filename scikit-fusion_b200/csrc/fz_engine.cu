@@ -399,7 +399,7 @@ class Engine : public EngineBase {
       TypeRec& t = *tp;
       t.gram_raw = small_.template as<double>() + off;
       off += (int64_t)t.k * t.k;
-      t.gram_rows_per_chunk = (int)std::max<int64_t>(64, (t.m_loc + 2 * sms - 1) / (2 * sms));
+      t.gram_rows_per_chunk = (int)std::max<int64_t>(64, (t.m_loc + 4 * sms - 1) / (4 * sms));   // ~4 resident blocks per SM hide the load latency
       t.gram_rows_per_chunk = ((t.gram_rows_per_chunk + 15) / 16) * 16;
       t.gram_chunks = (int)std::max<int64_t>(1, (t.m_loc + t.gram_rows_per_chunk - 1) / t.gram_rows_per_chunk);
       t.gram_part.alloc((size_t)t.gram_chunks * t.k * t.k * 8);
@@ -734,6 +734,8 @@ class Engine : public EngineBase {
     umma_attr<128, false>(); umma_attr<128, true>();
     umma_attr<192, false>(); umma_attr<192, true>();
     cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes);
+    cudaFuncSetAttribute(pinv_spd, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
+    cudaFuncSetAttribute(backbone_chain<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
   }
   // tensor-core product of a bf16 relation with a split factor:  C (M x k) = op(R) * Gs[g_row0 + ., :]
   void umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g_row0, T* C, int64_t ldc, int M, int K, int k, cudaStream_t st);
@@ -753,7 +755,7 @@ class Engine : public EngineBase {
       dim3 g(t.gram_chunks, nblk(t.k, 64), nblk(t.k, 64));
       gram_partial<T><<<g, 256, 0, st>>>(Gl, t.k, Gl, t.k, t.gram_part.template as<double>(), t.rows_loc, t.k, t.k,
                                          t.gram_rows_per_chunk, 0);
-      reduce_partials<<<nblk((long long)t.k * t.k, 256), 256, 0, st>>>(t.gram_part.template as<double>(), t.gram_raw, t.gram_chunks,
+      reduce_partials<<<nblk((long long)t.k * t.k, 32), 256, 0, st>>>(t.gram_part.template as<double>(), t.gram_raw, t.gram_chunks,
                                                                        (long long)t.k * t.k);
       launches += 2;
     }
@@ -784,7 +786,7 @@ class Engine : public EngineBase {
     dim3 g(r.m_chunks, nblk(Ti.k, 64), nblk(Tj.k, 64));
     gram_partial<T><<<g, 256, 0, st>>>(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.A.template as<T>(), Tj.k, r.M_part.template as<double>(),
                                        r.rows_loc, Ti.k, Tj.k, r.m_rows_per_chunk, 0);
-    reduce_partials<<<nblk((long long)Ti.k * Tj.k, 256), 256, 0, st>>>(r.M_part.template as<double>(), r.M_raw, r.m_chunks,
+    reduce_partials<<<nblk((long long)Ti.k * Tj.k, 32), 256, 0, st>>>(r.M_part.template as<double>(), r.M_raw, r.m_chunks,
                                                                        (long long)Ti.k * Tj.k);
     launches += 2;
   }
@@ -914,10 +916,10 @@ class Engine : public EngineBase {
       CUDA_OK(cudaStreamSynchronize(st));
       bb_mode_ = mode;
     }
-    pinv_spd<<<(unsigned)types_.size(), kChainThreads, 0, st>>>(pinv_jobs_.template as<PinvJob>());
+    pinv_spd<<<(unsigned)types_.size(), kChainThreads, kChainSmemBytes, st>>>(pinv_jobs_.template as<PinvJob>());
     ++launches;
     if (!bb_host_.empty()) {
-      backbone_chain<T><<<(unsigned)bb_host_.size(), kChainThreads, 0, st>>>(bb_jobs_.template as<BackboneJob<T>>());
+      backbone_chain<T><<<(unsigned)bb_host_.size(), kChainThreads, kChainSmemBytes, st>>>(bb_jobs_.template as<BackboneJob<T>>());
       ++launches;
     }
     type_sums<T><<<(unsigned)types_.size(), 256, 0, st>>>(sum_jobs_.template as<TypeSumJob<T>>());

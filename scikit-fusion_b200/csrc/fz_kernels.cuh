@@ -173,13 +173,30 @@ gram_partial(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, lo
   }
 }
 
-// out[i] = sum_c part[c][i]  in fixed chunk order (deterministic)
-__global__ void reduce_partials(const double* __restrict__ part, double* __restrict__ out, int n_chunks, long long elems) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= elems) return;
-  double s = 0.0;
-  for (int c = 0; c < n_chunks; ++c) s += part[(long long)c * elems + i];
-  out[i] = s;
+// out[i] = sum_c part[c][i], deterministic: block = 32 consecutive elements x 8 chunk lanes (warp w sums the
+// chunks w, w+8, ... in order), then the 8 lane sums are added in fixed order.  grid = ceil(elems / 32), 256 threads.
+__global__ void __launch_bounds__(256)
+reduce_partials(const double* __restrict__ part, double* __restrict__ out, int n_chunks, long long elems) {
+  __shared__ double lanes[8][32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const long long i = (long long)blockIdx.x * 32 + l;
+  double s0 = 0.0, s1 = 0.0;
+  if (i < elems) {
+    int c = w;
+    for (; c + 8 < n_chunks; c += 16) {
+      s0 += part[(long long)c * elems + i];
+      s1 += part[(long long)(c + 8) * elems + i];
+    }
+    if (c < n_chunks) s0 += part[(long long)c * elems + i];
+  }
+  lanes[w][l] = s0 + s1;
+  __syncthreads();
+  if (w == 0 && i < elems) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += lanes[k][l];
+    out[i] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -219,103 +236,121 @@ struct UpdArgs {
   const T* Dsum;
 };
 
-constexpr int kUpdRows = 32;
+constexpr int kUpdRows = 64;    // rows of the factor per block
+constexpr int kUpdSlab = 32;    // reduction slab staged in shared memory
 
-constexpr int kUpdSlab = 32;   // reduction slab (keeps fp64 tiles under the 48 KB static limit)
+// One (64 rows x 64 cols) output tile per block and q-tile; 256 threads, 4 x 4 outputs per thread:
+// per reduction step 4 broadcast reads of X and one 16-byte read of W feed 16 FMAs.
+template <class T>
+__device__ __forceinline__ void upd_accumulate(T (&acc)[4][4], const T (*Xs)[kUpdSlab + 1], const T (*Ws)[64 + 4], int ty, int tx,
+                                               int cmax) {
+  for (int cc = 0; cc < cmax; ++cc) {
+    T x[4], w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = Xs[ty * 4 + i][cc];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = Ws[cc][tx * 4 + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += x[i] * w[j];
+  }
+}
 
 template <class T>
 __global__ void __launch_bounds__(256)
 fused_update(const UpdArgs<T> a) {
   __shared__ T Xs[kUpdRows][kUpdSlab + 1];
-  __shared__ T Ws[kUpdSlab][64 + 1];
-  __shared__ T Ws2[kUpdSlab][64 + 1];
+  __shared__ __align__(16) T Ws[kUpdSlab][64 + 4];
   const int tid = threadIdx.x;
   const long long r0 = (long long)blockIdx.x * kUpdRows;
-  const int r = tid / 8;            // row inside the block (0..31)
-  const int qb = tid % 8;           // this thread's outputs: q = q0 + qb + 8*j, j = 0..7
-  const long long row = r0 + r;
+  const int ty = tid / 16, tx = tid % 16;
   const T eps = (T)2.220446049250313e-16;
 
+  auto load_x = [&](const T* X, long long ldx, int kx, int c0) {
+    for (int idx = tid; idx < kUpdRows * kUpdSlab; idx += 256) {
+      const int rr = idx / kUpdSlab, cc = idx % kUpdSlab;
+      T v = T(0);
+      if (r0 + rr < a.rows && c0 + cc < kx) v = X[(r0 + rr) * ldx + c0 + cc];
+      Xs[rr][cc] = v;
+    }
+  };
+  auto load_w = [&](const T* W, int kx, int c0, int q0) {
+    for (int idx = tid; idx < kUpdSlab * 64; idx += 256) {
+      const int cc = idx / 64, qq = idx % 64;
+      T v = T(0);
+      if (c0 + cc < kx && q0 + qq < a.kt) v = W[(long long)(c0 + cc) * a.kt + q0 + qq];
+      Ws[cc][qq] = v;
+    }
+  };
+
   for (int q0 = 0; q0 < a.kt; q0 += 64) {
-    T num[8], den[8];
+    T num[4][4], den[4][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { num[j] = T(0); den[j] = T(0); }
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { num[i][j] = T(0); den[i][j] = T(0); }
 
     // ---- relation terms: pos/neg parts of X W
     for (int t = 0; t < a.n_terms; ++t) {
       const UpdTerm<T> term = a.terms[t];
-      T acc[8];
+      T acc[4][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = T(0);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
       for (int c0 = 0; c0 < term.kx; c0 += kUpdSlab) {
-        for (int idx = tid; idx < kUpdRows * kUpdSlab; idx += 256) {
-          const int rr = idx / kUpdSlab, cc = idx % kUpdSlab;
-          T v = T(0);
-          if (r0 + rr < a.rows && c0 + cc < term.kx) v = term.X[(r0 + rr) * term.ldx + c0 + cc];
-          Xs[rr][cc] = v;
-        }
-        for (int idx = tid; idx < kUpdSlab * 64; idx += 256) {
-          const int cc = idx / 64, qq = idx % 64;
-          T v = T(0);
-          if (c0 + cc < term.kx && q0 + qq < a.kt) v = term.W[(long long)(c0 + cc) * a.kt + q0 + qq];
-          Ws[cc][qq] = v;
-        }
+        load_x(term.X, term.ldx, term.kx, c0);
+        load_w(term.W, term.kx, c0, q0);
         __syncthreads();
-        const int cmax = min(kUpdSlab, term.kx - c0);
-        for (int cc = 0; cc < cmax; ++cc) {
-          const T x = Xs[r][cc];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += x * Ws[cc][qb + 8 * j];
-        }
+        upd_accumulate<T>(acc, Xs, Ws, ty, tx, min(kUpdSlab, term.kx - c0));
         __syncthreads();
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        T v = acc[j];
-        if (a.scrub_terms) v = scrub(v);
-        T p, n;
-        sign_split(v, p, n);
-        num[j] += p;
-        den[j] += n;
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          T v = acc[i][j];
+          if (a.scrub_terms) v = scrub(v);
+          T pp, nn;
+          sign_split(v, pp, nn);
+          num[i][j] += pp;
+          den[i][j] += nn;
+        }
     }
-    // ---- G * Nsum and G * Dsum
-    for (int c0 = 0; c0 < a.kt; c0 += kUpdSlab) {
-      for (int idx = tid; idx < kUpdRows * kUpdSlab; idx += 256) {
-        const int rr = idx / kUpdSlab, cc = idx % kUpdSlab;
-        T v = T(0);
-        if (r0 + rr < a.rows && c0 + cc < a.kt) v = a.G[(r0 + rr) * a.ldg + c0 + cc];
-        Xs[rr][cc] = v;
-      }
-      for (int idx = tid; idx < kUpdSlab * 64; idx += 256) {
-        const int cc = idx / 64, qq = idx % 64;
-        T v = T(0), w = T(0);
-        if (c0 + cc < a.kt && q0 + qq < a.kt) {
-          v = a.Nsum[(long long)(c0 + cc) * a.kt + q0 + qq];
-          w = a.Dsum[(long long)(c0 + cc) * a.kt + q0 + qq];
-        }
-        Ws[cc][qq] = v;
-        Ws2[cc][qq] = w;
-      }
-      __syncthreads();
-      const int cmax = min(kUpdSlab, a.kt - c0);
-      for (int cc = 0; cc < cmax; ++cc) {
-        const T x = Xs[r][cc];
+    // ---- G * Nsum (numerator) and G * Dsum (denominator)
+    for (int pass = 0; pass < 2; ++pass) {
+      const T* W = pass == 0 ? a.Nsum : a.Dsum;
+      T acc[4][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          num[j] += x * Ws[cc][qb + 8 * j];
-          den[j] += x * Ws2[cc][qb + 8 * j];
-        }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+      for (int c0 = 0; c0 < a.kt; c0 += kUpdSlab) {
+        load_x(a.G, a.ldg, a.kt, c0);
+        load_w(W, a.kt, c0, q0);
+        __syncthreads();
+        upd_accumulate<T>(acc, Xs, Ws, ty, tx, min(kUpdSlab, a.kt - c0));
+        __syncthreads();
       }
-      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (pass == 0) num[i][j] += acc[i][j];
+          else den[i][j] += acc[i][j];
+        }
     }
     // ---- additive pairs + the update itself
-    if (row < a.rows) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int q = q0 + qb + 8 * j;
+    for (int i = 0; i < 4; ++i) {
+      const long long row = r0 + ty * 4 + i;
+      if (row >= a.rows) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = q0 + tx * 4 + j;
         if (q >= a.kt) continue;
-        T nu = num[j], de = den[j];
+        T nu = num[i][j], de = den[i][j];
         for (int s = 0; s < a.n_adds; ++s) {
           nu += a.adds[s].num[row * a.kt + q];
           de += a.adds[s].den[row * a.kt + q];

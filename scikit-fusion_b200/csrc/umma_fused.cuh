@@ -4,10 +4,11 @@
 // so the relation is streamed from HBM once per iteration instead of once per product.
 //
 // CTA = a PAIR of 128-row blocks (256 rows of R) x a range of 128-column tiles.  Per column tile c:
-//   TMA   : R[r0+128t .. , c] for t = 0,1 (32 KB each, 128B swizzle) and the two 64-row halves of the Gs_j tile
+//   TMA   : R[r0+128t .. , c] for t = 0,1 (32 KB each, 128B swizzle; warp 0) and the two 64-row halves of the Gs_j
+//           tile (warp 6, a separate producer so factor operands are prefetched independently of relation stages)
 //   MMA   : A_acc[t] += R_tile (K-major A)  * Gs_j[c]   (MN-major B)     8 x UMMA 128x128x16 per row block
 //           B_acc[c&1] (+)= R_tile^T (MN-major A view of the same bytes) * Gs_i[t] (resident, MN-major B)
-//           issue order  A(t0,k0-3) A(t1,k0-3) | A(t0,k4-7) B(t0) | A(t1,k4-7) B(t1)  releases each Gs_j half early
+//           issue order  A(t0) B(t0) | A(t1) B(t1): a relation stage is held for just its own 16 MMAs
 //   epilog: once both row blocks of tile c are multiplied, 4 warps drain B_acc[c&1] from TMEM, add the split terms,
 //           stage the 128 x k fp32 partial in shared memory (swizzled) and hand it to the TMA unit as
 //           cp.reduce.async.bulk.tensor ... .add  -- the reduction happens in L2, the SM's LSU never sees it --
@@ -37,7 +38,7 @@ struct FusedParams {
   int probe_skip_flush;// developer probe only (wrong results): bit0 = no reductions, bit1 = no B-product MMAs, bit2 = no A-product MMAs
 };
 
-constexpr int kFuThreads = 192;
+constexpr int kFuThreads = 224;   // warp 0: R producer | 1: MMA | 2..5: epilogue | 6: Gs producer
 constexpr int kFuTile = 128;
 constexpr int kFuRStages = 3;
 constexpr int kFuGjSlots = 3;
@@ -99,35 +100,38 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
+    // ---------------------------------------------------------------- TMA producer: relation tiles
+    if (lane == 0) {
+      int it = 0;
+      for (int c = 0; c < n_tiles; ++c) {
+        const int col0 = (tile_begin + c) * kFuTile;
+        for (int t = 0; t < 2; ++t, ++it) {
+          const int s = it % kFuRStages;
+          ptx::mbar_wait(&r_empty[s], ((it / kFuRStages) & 1) ^ 1);
+          ptx::mbar_expect_tx(&r_full[s], kFuTileBytes);
+          for (int ch = 0; ch < 2; ++ch)
+            ptx::tma_load_2d(r_st + s * kFuTileBytes + ch * 16384, &tmR, &r_full[s], col0 + ch * 64, r0 + t * kFuTile,
+                             ptx::kEvictFirst);
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ---------------------------------------------------------------- TMA producer: factor operands
+    // (own warp so that a Gs_j half is requested the moment its ring slot frees up, ~1.25 tiles ahead of use,
+    //  instead of queueing behind relation tiles that wait for a free stage)
     if (lane == 0 && n_tiles > 0) {
       ptx::mbar_expect_tx(gi_full, 2 * kFuTileBytes);            // resident Gs_i tiles of the two row blocks
       for (int t = 0; t < 2; ++t)
         for (int ch = 0; ch < 2; ++ch)
           ptx::tma_load_2d(gi_st + t * kFuTileBytes + ch * 16384, &tmGi, gi_full, ch * 64, p.gi_row0 + r0 + t * kFuTile,
                            ptx::kEvictLast);
-      int it = 0;
-      for (int c = 0; c < n_tiles; ++c) {
-        const int col0 = (tile_begin + c) * kFuTile;
-        for (int h = 0; h < 2; ++h) {
-          const int i = 2 * c + h;
-          const int slot = i % kFuGjSlots;
-          ptx::mbar_wait(&gj_empty[slot], ((i / kFuGjSlots) & 1) ^ 1);
-          ptx::mbar_expect_tx(&gj_full[slot], kFuHalfBytes);
-          for (int ch = 0; ch < 2; ++ch)
-            ptx::tma_load_2d(gj_st + slot * kFuHalfBytes + ch * 8192, &tmGj, &gj_full[slot], ch * 64, col0 + h * 64,
-                             ptx::kEvictLast);
-          if (h == 0) {                                          // the two R tiles go between the Gs_j halves
-            for (int t = 0; t < 2; ++t, ++it) {
-              const int s = it % kFuRStages;
-              ptx::mbar_wait(&r_empty[s], ((it / kFuRStages) & 1) ^ 1);
-              ptx::mbar_expect_tx(&r_full[s], kFuTileBytes);
-              for (int ch = 0; ch < 2; ++ch)
-                ptx::tma_load_2d(r_st + s * kFuTileBytes + ch * 16384, &tmR, &r_full[s], col0 + ch * 64, r0 + t * kFuTile,
-                                 ptx::kEvictFirst);
-            }
-          }
-        }
+      for (int i = 0; i < 2 * n_tiles; ++i) {
+        const int col0 = (tile_begin + (i >> 1)) * kFuTile + (i & 1) * 64;
+        const int slot = i % kFuGjSlots;
+        ptx::mbar_wait(&gj_empty[slot], ((i / kFuGjSlots) & 1) ^ 1);
+        ptx::mbar_expect_tx(&gj_full[slot], kFuHalfBytes);
+        for (int ch = 0; ch < 2; ++ch)
+          ptx::tma_load_2d(gj_st + slot * kFuHalfBytes + ch * 8192, &tmGj, &gj_full[slot], ch * 64, col0, ptx::kEvictLast);
       }
     }
   } else if (warp == 1) {
@@ -149,7 +153,8 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
         const uint32_t gi0 = ptx::smem_u32(gi_st), gi1 = gi0 + kFuTileBytes;
         const uint32_t bacc = tmem_base + 256 + gs * 128;
         it += 2;
-        // ---- first Gs_j half: A_acc[t] over the tile's columns 0..63
+        // ---- row block 0: A-product over both Gs_j halves, then the transposed product; the relation stage is
+        //      released as soon as its 16 MMAs retire (short stage hold time keeps two tiles in flight from HBM)
         ptx::mbar_wait(&gj_full[slot0], (i0 / kFuGjSlots) & 1);
         ptx::mbar_wait(&r_full[s0], ph0);
         ptx::tc_fence_after();
@@ -158,6 +163,22 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
           for (int ks = 0; ks < 4; ++ks)
             ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(rt0 + ks * 32, 16, 1024),
                            ptx::smem_desc_sw128(g0 + ks * 2048, 8192, 1024), idesc_a, (c | ks) != 0);
+        ptx::mbar_wait(&gj_full[slot1], (i1 / kFuGjSlots) & 1);
+        ptx::tc_fence_after();
+        if (do_a)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(rt0 + 16384 + ks * 32, 16, 1024),
+                           ptx::smem_desc_sw128(g1 + ks * 2048, 8192, 1024), idesc_a, 1);
+        ptx::mbar_wait(&bacc_empty[gs], ((c >> 1) & 1) ^ 1);       // epilogue has drained this B_acc buffer
+        ptx::tc_fence_after();
+        if (do_b)
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            ptx::umma_bf16(bacc, ptx::smem_desc_sw128(rt0 + ks * 2048, 16384, 1024),
+                           ptx::smem_desc_sw128(gi0 + ks * 2048, 16384, 1024), idesc_b, ks != 0);
+        ptx::umma_commit(&r_empty[s0]);
+        // ---- row block 1; each Gs_j half goes back to the ring right after its last use
         ptx::mbar_wait(&r_full[s1], ph1);
         ptx::tc_fence_after();
         if (do_a)
@@ -166,22 +187,6 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
             ptx::umma_bf16(tmem_base + 128, ptx::smem_desc_sw128(rt1 + ks * 32, 16, 1024),
                            ptx::smem_desc_sw128(g0 + ks * 2048, 8192, 1024), idesc_a, (c | ks) != 0);
         ptx::umma_commit(&gj_empty[slot0]);
-        // ---- second half (columns 64..127) of row block 0, then its transposed product
-        ptx::mbar_wait(&gj_full[slot1], (i1 / kFuGjSlots) & 1);
-        ptx::mbar_wait(&bacc_empty[gs], ((c >> 1) & 1) ^ 1);       // epilogue has drained this B_acc buffer
-        ptx::tc_fence_after();
-        if (do_a)
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(rt0 + 16384 + ks * 32, 16, 1024),
-                           ptx::smem_desc_sw128(g1 + ks * 2048, 8192, 1024), idesc_a, 1);
-        if (do_b)
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            ptx::umma_bf16(bacc, ptx::smem_desc_sw128(rt0 + ks * 2048, 16384, 1024),
-                           ptx::smem_desc_sw128(gi0 + ks * 2048, 16384, 1024), idesc_b, ks != 0);
-        ptx::umma_commit(&r_empty[s0]);
-        // ---- same for row block 1
         if (do_a)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
