@@ -250,12 +250,16 @@ def e2e_leg(args, torch, dist, fzd, _capi, R_dev, G0, types, sizes, ranks, world
         return {"value": None, "unit": "it/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                 "note": "host RAM too small to stage the relations (%.0f GB needed, %.0f GB available)" % (need / 1e9, avail / 1e9)}
     # stage: device -> pinned host (outside the timed region), then drop the device copies
+    t_stage = time.perf_counter()
     host = {}
     for key, mats in R_dev.items():
         h = torch.empty(mats[0].shape, dtype=torch.bfloat16, pin_memory=True)
         h.copy_(mats[0])
         host[key] = [h]
     torch.cuda.synchronize(dev)
+    if rank == 0:
+        print("[bench] staged %.1f GB of relations in pinned host memory in %.1f s" % (need / 1e9, time.perf_counter() - t_stage),
+              file=sys.stderr, flush=True)
     for key in list(R_dev.keys()):
         R_dev[key] = None
     R_dev.clear()

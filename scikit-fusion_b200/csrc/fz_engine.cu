@@ -262,6 +262,7 @@ class Engine : public EngineBase {
   int device_;
   int world_ = 1, rank_ = 0;
   int terms_ = 2;
+  int sm_count_ = 148;
   bool fused_ = true;       // single-pass A/B kernel for bf16 relations (needs terms_ == 2); FZ_NO_FUSED=1 disables
   int fused_csplit_ = 0;    // column splits of the fused kernel (0 = automatic); FZ_FUSED_CSPLIT overrides
   bool finalized_ = false;
@@ -388,6 +389,7 @@ class Engine : public EngineBase {
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device_));
     const int sms = prop.multiProcessorCount;
+    sm_count_ = sms;
     // fp64 all-reduce buffer: [gram_t ...][M_r ...]
     small_count_ = 0;
     for (auto& t : types_) small_count_ += (int64_t)t->k * t->k;
@@ -1022,8 +1024,20 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   const int tiles = (int)((r.cols + kFuTile - 1) / kFuTile);
   int splits = fused_csplit_;
   if (splits <= 0) {
-    splits = (148 * 6 + pairs - 1) / pairs;            // ~6 CTAs per SM in total
-    splits = std::min(splits, std::max(1, tiles / 8)); // but keep >= 8 column tiles per CTA
+    // Pick the column split that fills whole waves of one CTA per SM: score = wave efficiency x (1 - fixed per-CTA
+    // cost of ~3 tile-times for pipeline fill, resident-operand load and the final A flush).
+    double best = -1.0;
+    splits = 1;
+    const int max_splits = std::max(1, std::min(tiles, 64));
+    for (int cand = 1; cand <= max_splits; ++cand) {
+      const int tps = (tiles + cand - 1) / cand;
+      const int eff_splits = (tiles + tps - 1) / tps;
+      const double ctas = (double)pairs * eff_splits;
+      const double waves = ctas / sm_count_;
+      const double wave_eff = waves / std::ceil(waves);
+      const double score = wave_eff * (1.0 - 3.0 / (tps + 3.0));
+      if (score > best + 1e-9) { best = score; splits = eff_splits; }
+    }
   }
   splits = std::max(1, std::min(splits, tiles));
   p.tiles_per_split = (tiles + splits - 1) / splits;

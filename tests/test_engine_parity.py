@@ -220,3 +220,27 @@ def test_dicty_config_fp32_against_oracle(algo):
         assert err < 1e-3, "S%s relFro=%.3g" % (key, err)
     obj_o, obj_g = oracle.objective(case["R"], Go, So)[0], oracle.objective(case["R"], G, S)[0]
     assert abs(obj_o - obj_g) / obj_o < 1e-5
+
+
+def test_transform_on_tensor_core_path_against_oracle():
+    """BASELINE config C5 in miniature: project new rows of one type against a fitted 3-type model with the new
+    relations stored in bf16 (tcgen05 product R_new (G_j S^T) with a 2-term split of the frozen operand)."""
+    from skfusion.fusion import solver
+    n, n_new, k = 512, 384, 64
+    types, ranks, R = oracle.hashed_graph(n, n_types=3, rank=k, storage="bfloat16")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Go, So = oracle.dfmf(R, {}, types, ranks, max_iter=10, init_type="random", random_state=np.random.RandomState(0))
+    tags = {t: cases.Tag(t) for t in types}
+    G = {(tags[t], tags[t]): Go[t, t] for t in types}
+    S = {(tags[a], tags[b]): So[a, b] for (a, b) in So}
+    R_new = {(tags[0], tags[1]): [oracle.bf16_round(oracle.hashed_uniform(77, n_new, n))],
+             (tags[0], tags[2]): [oracle.bf16_round(oracle.hashed_uniform(78, n_new, n))]}
+    rk = {tags[t]: k for t in types}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = oracle.transform(R_new, {}, tags[0], rk, G, S, max_iter=40, init_type="random", random_state=np.random.RandomState(3))
+        got = solver.transform(R_new, {}, tags[0], rk, G, S, max_iter=40, init_type="random", random_state=np.random.RandomState(3),
+                               dtype="float32", storage="bfloat16", split_terms=2)
+    assert got.shape == (n_new, k)
+    assert rel_fro(ref, got) < 1e-3
