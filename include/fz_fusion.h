@@ -86,6 +86,12 @@ int fz_iterate(fz_engine* e, int algo, int n_iters, void* stream);
  * [all-gather factors].  fz_iterate == products + update when world == 1. */
 int fz_phase_products(fz_engine* e, int algo, void* stream);
 int fz_phase_update(fz_engine* e, int algo, void* stream);
+/* fz_phase_products in pieces (dfmf): begin (Gram partials, operand forms), one call per relation (its A, B partial
+ * and G_i^T A), end (constraint products).  Lets the caller overlap the reduce-scatter of relation r with the
+ * streamed products of relation r+1. */
+int fz_phase_products_begin(fz_engine* e, int algo, void* stream);
+int fz_phase_product_relation(fz_engine* e, int algo, int rel, void* stream);
+int fz_phase_products_end(fz_engine* e, int algo, void* stream);
 /* communication buffers (device pointers, valid after fz_finalize) */
 int fz_comm_small(fz_engine* e, void** ptr, int64_t* count_f64);               /* all-reduce, fp64 */
 int fz_comm_bpartial(fz_engine* e, int rel, void** full_ptr, void** local_ptr, /* reduce-scatter  */

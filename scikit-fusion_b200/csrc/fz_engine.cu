@@ -128,6 +128,9 @@ class EngineBase {
   virtual void iterate(int algo, int n_iters, cudaStream_t st) = 0;
   virtual void phase_products(int algo, cudaStream_t st) = 0;
   virtual void phase_update(int algo, cudaStream_t st) = 0;
+  virtual void phase_products_begin(int algo, cudaStream_t st) = 0;
+  virtual void phase_product_relation(int algo, int rel, cudaStream_t st) = 0;
+  virtual void phase_products_end(int algo, cudaStream_t st) = 0;
   virtual void comm_small(void** ptr, int64_t* count) = 0;
   virtual void comm_bpartial(int rel, void** full, void** local, int64_t* local_count, int* dtype) = 0;
   virtual void comm_factor(int t, void** full, int64_t* local_count, int* dtype) = 0;
@@ -401,7 +404,7 @@ class Engine : public EngineBase {
       TypeRec& t = *tp;
       t.gram_raw = small_.template as<double>() + off;
       off += (int64_t)t.k * t.k;
-      t.gram_rows_per_chunk = (int)std::max<int64_t>(64, (t.m_loc + 4 * sms - 1) / (4 * sms));   // ~4 resident blocks per SM hide the load latency
+      t.gram_rows_per_chunk = (int)std::max<int64_t>(64, (t.m_loc + 2 * sms - 1) / (2 * sms));
       t.gram_rows_per_chunk = ((t.gram_rows_per_chunk + 15) / 16) * 16;
       t.gram_chunks = (int)std::max<int64_t>(1, (t.m_loc + t.gram_rows_per_chunk - 1) / t.gram_rows_per_chunk);
       t.gram_part.alloc((size_t)t.gram_chunks * t.k * t.k * 8);
@@ -493,15 +496,31 @@ class Engine : public EngineBase {
         if (!rp->theta) { product_A(*rp, st); reduce_M(*rp, st); }
       return;  // the second half (imputation, A/B on the completed R) runs in phase_update
     }
+    phase_products_begin(algo, st);
+    for (size_t r = 0; r < rels_.size(); ++r) phase_product_relation(algo, (int)r, st);
+    phase_products_end(algo, st);
+  }
+
+  // The same phase in pieces, so that a sharded caller can start the reduce-scatter of one relation's B partial
+  // while the next relation is still being streamed (skfusion/fusion/distributed.py).
+  void phase_products_begin(int algo, cudaStream_t st) override {
+    need_final();
+    check_factors();
+    if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_UNSUPPORTED, "piecewise products are for dfmf");
     grams(st);
-    for (auto& rp : rels_) {
-      if (rp->theta) continue;
-      if (!product_AB_fused(*rp, st)) {
-        product_A(*rp, st);
-        product_B(*rp, st);
-      }
-      reduce_M(*rp, st);
+  }
+  void phase_product_relation(int algo, int rel, cudaStream_t st) override {
+    (void)algo;
+    RelRec& r = relation(rel);
+    if (r.theta) return;
+    if (!product_AB_fused(r, st)) {
+      product_A(r, st);
+      product_B(r, st);
     }
+    reduce_M(r, st);
+  }
+  void phase_products_end(int algo, cudaStream_t st) override {
+    (void)algo;
     theta_products(st);
     CUDA_OK(cudaGetLastError());
   }
@@ -1167,6 +1186,11 @@ int fz_finalize(fz_engine* e) { FZ_GUARD(e, e->impl->finalize()) }
 int fz_iterate(fz_engine* e, int algo, int n_iters, void* stream) { FZ_GUARD(e, e->impl->iterate(algo, n_iters, (cudaStream_t)stream)) }
 int fz_phase_products(fz_engine* e, int algo, void* stream) { FZ_GUARD(e, e->impl->phase_products(algo, (cudaStream_t)stream)) }
 int fz_phase_update(fz_engine* e, int algo, void* stream) { FZ_GUARD(e, e->impl->phase_update(algo, (cudaStream_t)stream)) }
+int fz_phase_products_begin(fz_engine* e, int algo, void* stream) { FZ_GUARD(e, e->impl->phase_products_begin(algo, (cudaStream_t)stream)) }
+int fz_phase_product_relation(fz_engine* e, int algo, int rel, void* stream) {
+  FZ_GUARD(e, e->impl->phase_product_relation(algo, rel, (cudaStream_t)stream))
+}
+int fz_phase_products_end(fz_engine* e, int algo, void* stream) { FZ_GUARD(e, e->impl->phase_products_end(algo, (cudaStream_t)stream)) }
 int fz_comm_small(fz_engine* e, void** ptr, int64_t* count) { FZ_GUARD(e, e->impl->comm_small(ptr, count)) }
 int fz_comm_bpartial(fz_engine* e, int rel, void** full_ptr, void** local_ptr, int64_t* local_count, int* dtype) {
   FZ_GUARD(e, e->impl->comm_bpartial(rel, full_ptr, local_ptr, local_count, dtype))

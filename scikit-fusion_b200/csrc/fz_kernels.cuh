@@ -119,8 +119,10 @@ template <class T>
 __global__ void __launch_bounds__(256)
 gram_partial(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, long long ldy, double* __restrict__ part,
              long long n_rows, int ka, int kb, int rows_per_chunk, int scrub_inputs) {
-  __shared__ double Xs[16][64 + 2];
-  __shared__ double Ys[16][64 + 2];
+  // 16-row slabs, double-buffered in shared memory; the next slab's global loads are issued into registers
+  // before the current slab is multiplied, so DRAM/L2 latency overlaps the fp64 FMAs.
+  __shared__ double Xs[2][16][64 + 2];
+  __shared__ double Ys[2][16][64 + 2];
   const int tid = threadIdx.x;
   const int a0 = blockIdx.y * 64, b0 = blockIdx.z * 64;
   const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
@@ -131,7 +133,9 @@ gram_partial(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, lo
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+
+  double px[4], py[4];
+  auto fetch = [&](long long r0) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int idx = tid + e * 256;
@@ -142,23 +146,37 @@ gram_partial(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, lo
         if (b0 + cc < kb) yv = (double)Y[(r0 + rr) * ldy + b0 + cc];
         if (scrub_inputs) { xv = scrub(xv); yv = scrub(yv); }
       }
-      Xs[rr][cc] = xv;
-      Ys[rr][cc] = yv;
+      px[e] = xv;
+      py[e] = yv;
     }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      Xs[buf][idx / 64][idx % 64] = px[e];
+      Ys[buf][idx / 64][idx % 64] = py[e];
+    }
+  };
+  int buf = 0;
+  if (r_begin < r_end) fetch(r_begin);
+  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+    stash(buf);
     __syncthreads();
+    if (r0 + 16 < r_end) fetch(r0 + 16);
 #pragma unroll
     for (int rr = 0; rr < 16; ++rr) {
       double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = Xs[rr][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) a[i] = Xs[buf][rr][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Ys[rr][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = Ys[buf][rr][tx * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
     }
-    __syncthreads();
+    buf ^= 1;   // the other buffer was last read two iterations ago, behind the barrier above
   }
   double* out = part + (long long)blockIdx.x * ka * kb;
 #pragma unroll

@@ -22,7 +22,7 @@ FZ_DFMF, FZ_DFMC = 0, 1
 SYMBOLS = [
     "fz_create", "fz_destroy", "fz_last_error", "fz_version", "fz_launch_count", "fz_set_shard", "fz_add_type",
     "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_finalize", "fz_iterate",
-    "fz_phase_products", "fz_phase_update", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
+    "fz_phase_products", "fz_phase_update", "fz_phase_products_begin", "fz_phase_product_relation", "fz_phase_products_end", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
     "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete",
     "fz_fill_uniform", "fz_profile", "fz_profile_read",
 ]
@@ -87,6 +87,9 @@ def lib():
         "fz_iterate": (i32, [vp, i32, i32, vp]),
         "fz_phase_products": (i32, [vp, i32, vp]),
         "fz_phase_update": (i32, [vp, i32, vp]),
+        "fz_phase_products_begin": (i32, [vp, i32, vp]),
+        "fz_phase_product_relation": (i32, [vp, i32, i32, vp]),
+        "fz_phase_products_end": (i32, [vp, i32, vp]),
         "fz_comm_small": (i32, [vp, c_void_pp, ctypes.POINTER(i64)]),
         "fz_comm_bpartial": (i32, [vp, i32, c_void_pp, c_void_pp, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
         "fz_comm_factor": (i32, [vp, i32, c_void_pp, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
@@ -237,6 +240,15 @@ class Engine(object):
 
     def phase_products(self, algo, stream=0):
         self._ck(self._L.fz_phase_products(self._h, algo, ctypes.c_void_p(stream)))
+
+    def phase_products_begin(self, algo, stream=0):
+        self._ck(self._L.fz_phase_products_begin(self._h, algo, ctypes.c_void_p(stream)))
+
+    def phase_product_relation(self, algo, rel, stream=0):
+        self._ck(self._L.fz_phase_product_relation(self._h, algo, int(rel), ctypes.c_void_p(stream)))
+
+    def phase_products_end(self, algo, stream=0):
+        self._ck(self._L.fz_phase_products_end(self._h, algo, ctypes.c_void_p(stream)))
 
     def phase_update(self, algo, stream=0):
         self._ck(self._L.fz_phase_update(self._h, algo, ctypes.c_void_p(stream)))

@@ -31,9 +31,11 @@ class Collectives(object):
     def all_reduce(self, t):
         self.dist.all_reduce(t, group=self.group)
 
-    def reduce_scatter(self, local, full):
+    def reduce_scatter(self, local, full, async_op=False):
+        """async_op (NCCL only): returns a work handle; the collective runs on NCCL's stream behind the work already
+        enqueued on the current stream, so later kernels of the current stream overlap it."""
         if self.native_rs:
-            self.dist.reduce_scatter_tensor(local, full, group=self.group)
+            return self.dist.reduce_scatter_tensor(local, full, group=self.group, async_op=async_op)
         else:  # gloo has no reduce-scatter: all-reduce and keep this rank's chunk
             self.dist.all_reduce(full, group=self.group)
             n = local.numel()
@@ -50,13 +52,27 @@ class Collectives(object):
 
 
 def run_iterations(shard, coll, n_iters):
-    """The sharded hot loop.  ``shard`` provides products(), update() and the comm buffers."""
+    """The sharded hot loop.  ``shard`` provides products(), update() and the comm buffers.  When the shard can
+    run its products relation by relation and the backend is NCCL, the reduce-scatter of relation r is put in
+    flight while relation r+1 is streamed."""
+    piecewise = coll.world > 1 and getattr(coll, "native_rs", False) and hasattr(shard, "product_relation")
     for _ in range(n_iters):
-        shard.products()
-        if coll.world > 1:
+        if piecewise:
+            shard.products_begin()
+            pending = []
+            for r, (full, local) in enumerate(shard.bpartials()):
+                shard.product_relation(r)
+                pending.append(coll.reduce_scatter(local, full, async_op=True))
+            shard.products_end()
             coll.all_reduce(shard.small())
-            for full, local in shard.bpartials():
-                coll.reduce_scatter(local, full)
+            for work in pending:
+                work.wait()
+        else:
+            shard.products()
+            if coll.world > 1:
+                coll.all_reduce(shard.small())
+                for full, local in shard.bpartials():
+                    coll.reduce_scatter(local, full)
         shard.update()
         if coll.world > 1:
             for full, local in shard.factors():
@@ -97,6 +113,15 @@ class CudaShard(object):
 
     def products(self):
         self.engine.phase_products(self.algo, self._stream())
+
+    def products_begin(self):
+        self.engine.phase_products_begin(self.algo, self._stream())
+
+    def product_relation(self, rel):
+        self.engine.phase_product_relation(self.algo, rel, self._stream())
+
+    def products_end(self):
+        self.engine.phase_products_end(self.algo, self._stream())
 
     def update(self):
         self.engine.phase_update(self.algo, self._stream())
