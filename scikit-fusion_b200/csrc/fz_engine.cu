@@ -266,6 +266,11 @@ class Engine : public EngineBase {
   int world_ = 1, rank_ = 0;
   int terms_ = 2;
   int sm_count_ = 148;
+  // auxiliary stream: the fp64 reductions (Gram, G_i^T A) run beside the streamed products and fill their tails
+  cudaStream_t aux_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+  std::vector<cudaEvent_t> ev_rel_;
+  bool use_aux_ = true;      // FZ_NO_AUX=1 keeps everything on the caller's stream
   bool fused_ = true;       // single-pass A/B kernel for bf16 relations (needs terms_ == 2); FZ_NO_FUSED=1 disables
   int fused_csplit_ = 0;    // column splits of the fused kernel (0 = automatic); FZ_FUSED_CSPLIT overrides
   bool finalized_ = false;
@@ -283,6 +288,12 @@ class Engine : public EngineBase {
 
  public:
   explicit Engine(int device) : device_(device) {}
+  ~Engine() override {
+    if (aux_) cudaStreamDestroy(aux_);
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
+    if (ev_join_) cudaEventDestroy(ev_join_);
+    for (auto e : ev_rel_) cudaEventDestroy(e);
+  }
   int compute_dtype() const override { return kDT; }
 
   void set_shard(int world, int rank) override {
@@ -460,6 +471,14 @@ class Engine : public EngineBase {
     if (const char* nf = getenv("FZ_NO_FUSED")) fused_ = !(nf[0] == '1');
     if (const char* cs = getenv("FZ_FUSED_CSPLIT")) fused_csplit_ = atoi(cs);
     if (terms_ != 2) fused_ = false;
+    if (const char* na = getenv("FZ_NO_AUX")) use_aux_ = !(na[0] == '1');
+    if (use_aux_) {
+      CUDA_OK(cudaStreamCreateWithFlags(&aux_, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+      ev_rel_.resize(rels_.size());
+      for (auto& e : ev_rel_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     build_job_tables();
     // opt in to the large dynamic shared memory of the tensor-core kernels
     set_umma_attrs();
@@ -507,7 +526,12 @@ class Engine : public EngineBase {
     need_final();
     check_factors();
     if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_UNSUPPORTED, "piecewise products are for dfmf");
-    grams(st);
+    if (!use_aux_) { grams(st); return; }
+    for (auto& tp : types_)
+      if (tp->need_gs) split(*tp, st);                 // operand forms first: every streamed product needs them
+    CUDA_OK(cudaEventRecord(ev_fork_, st));
+    CUDA_OK(cudaStreamWaitEvent(aux_, ev_fork_, 0));
+    for (auto& tp : types_) gram_of(*tp, aux_);        // Gram matrices beside the first streamed products
   }
   void phase_product_relation(int algo, int rel, cudaStream_t st) override {
     (void)algo;
@@ -517,11 +541,18 @@ class Engine : public EngineBase {
       product_A(r, st);
       product_B(r, st);
     }
-    reduce_M(r, st);
+    if (!use_aux_) { reduce_M(r, st); return; }
+    CUDA_OK(cudaEventRecord(ev_rel_[rel], st));        // A_ij is complete here
+    CUDA_OK(cudaStreamWaitEvent(aux_, ev_rel_[rel], 0));
+    reduce_M(r, aux_);                                 // G_i^T A_ij overlaps the next relation's stream
   }
   void phase_products_end(int algo, cudaStream_t st) override {
     (void)algo;
     theta_products(st);
+    if (use_aux_) {
+      CUDA_OK(cudaEventRecord(ev_join_, aux_));
+      CUDA_OK(cudaStreamWaitEvent(st, ev_join_, 0));
+    }
     CUDA_OK(cudaGetLastError());
   }
 
@@ -768,17 +799,19 @@ class Engine : public EngineBase {
   }
 
   // Gram matrices of the current factors over the local rows (+ bf16 operand form where needed)
+  void gram_of(TypeRec& t, cudaStream_t st) {
+    const T* Gl = cur(t) + t.row0 * t.k;
+    dim3 g(t.gram_chunks, nblk(t.k, 64), nblk(t.k, 64));
+    gram_partial<T><<<g, 256, 0, st>>>(Gl, t.k, Gl, t.k, t.gram_part.template as<double>(), t.rows_loc, t.k, t.k,
+                                       t.gram_rows_per_chunk, 0);
+    reduce_partials<<<nblk((long long)t.k * t.k, 32), 256, 0, st>>>(t.gram_part.template as<double>(), t.gram_raw, t.gram_chunks,
+                                                                     (long long)t.k * t.k);
+    launches += 2;
+  }
   void grams(cudaStream_t st) {
     for (auto& tp : types_) {
-      TypeRec& t = *tp;
-      if (t.need_gs) split(t, st);
-      const T* Gl = cur(t) + t.row0 * t.k;
-      dim3 g(t.gram_chunks, nblk(t.k, 64), nblk(t.k, 64));
-      gram_partial<T><<<g, 256, 0, st>>>(Gl, t.k, Gl, t.k, t.gram_part.template as<double>(), t.rows_loc, t.k, t.k,
-                                         t.gram_rows_per_chunk, 0);
-      reduce_partials<<<nblk((long long)t.k * t.k, 32), 256, 0, st>>>(t.gram_part.template as<double>(), t.gram_raw, t.gram_chunks,
-                                                                       (long long)t.k * t.k);
-      launches += 2;
+      if (tp->need_gs) split(*tp, st);
+      gram_of(*tp, st);
     }
   }
 
