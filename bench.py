@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=4096, help="objects per type of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "readme3", "dicty"],
+                    help="synthetic = the contract workload; readme3 / dicty = the small BASELINE configs C1 / C2 "
+                         "(latency-bound; informational line, N=1 only)")
     return ap.parse_args()
 
 
@@ -298,8 +301,59 @@ def e2e_leg(args, torch, dist, fzd, _capi, R_dev, G0, types, sizes, ranks, world
                     "(once per fit) + iterations + download of all factors and backbones, per rank" % args.steps}
 
 
+def small_workload(args):
+    """BASELINE configs C1 (README 3-type graph) and C2 (dicty): tiny, launch-latency-bound problems.  Prints the
+    engine's it/s (fp32 engine, whole loop in one C call, CUDA events) next to the oracle's on the host."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    import fusion_oracle as oracle
+    from skfusion import _capi
+    case = cases.dicty_case() if args.workload == "dicty" else cases.fit_cases()["readme3"]
+    sizes = oracle.count_objects(case["R"])
+    import warnings
+    warnings.simplefilter("ignore")
+    G0 = oracle.initialize(case["types"], sizes, case["ranks"], {k: v[0] for k, v in case["R"].items()}, case["init_type"],
+                           np.random.RandomState(0))
+    eng = _capi.Engine(0, "float32")
+    tid = {t: eng.add_type(sizes[t], case["ranks"][t]) for t in case["types"]}
+    for blocks in (case["R"], case["Theta"]):
+        for (a, b), mats in blocks.items():
+            for m in mats:
+                eng.add_relation(tid[a], tid[b], m)
+    for t in case["types"]:
+        eng.set_factor(tid[t], G0[t, t])
+    eng.finalize()
+    st = torch.cuda.current_stream().cuda_stream
+    eng.iterate(_capi.FZ_DFMF, max(3, args.warmup), st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launches
+    e0.record()
+    eng.iterate(_capi.FZ_DFMF, args.steps, st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = eng.launches - l0
+    eng.close()
+    stamps = []
+    oracle.dfmf(case["R"], case["Theta"], case["types"], case["ranks"], max_iter=args.steps + 2, G0=G0,
+                callback=lambda G, S, it: stamps.append(time.perf_counter()))
+    cpu_it = 1.0 / float(np.median(np.diff(stamps)))
+    print(json.dumps({"metric": "DFMF iterations/sec, BASELINE config %s" % args.workload, "value": round(1000.0 / ms, 1),
+                      "unit": "it/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": round(ms, 4), "dtype": "f32",
+                      "gpu_launches": launches, "launches_per_step": launches / float(args.steps),
+                      "cpu_baseline": {"value": round(cpu_it, 1), "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "oracle dfmf on the same inputs, all host BLAS threads"},
+                      "note": "latency-bound: no roofline claim (SURVEY.md 8d)"}))
+
+
 def main():
     args = parse()
+    if args.workload != "synthetic":
+        small_workload(args)
+        return
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         if rank != 0:
