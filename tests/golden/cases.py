@@ -88,3 +88,32 @@ def dicty_case(path=None):
                 ranks={"Gene": 50, "GO term": 15, "Experimental condition": 5},
                 R={("Gene", "GO term"): [ann], ("Gene", "Experimental condition"): [expr]},
                 Theta={("Gene", "Gene"): [ppi]}, M=None, init_type="random_vcol", seed=0, max_iter=50)
+
+
+def movielens_case(path=None):
+    """BASELINE config C3 (examples/movielens_completion.py:20-86): users x movies ratings scaled to [0, 1] with
+    the unknown (and 10 % hidden) entries masked and mean-filled, movies x genres, movies x actors; ranks
+    max(int(0.05 n), 5).  Returned at the function-level seam: R / M / Theta as Dfmc.fuse would marshal them."""
+    import os
+    path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "movielens_matrices.npz")
+    z = np.load(path)
+    n_u, n_m, n_g, n_a = [int(v) for v in z["shape"]]
+    R12 = -np.ones((n_u, n_m))
+    R12[z["r_u"], z["r_m"]] = z["r_v"].astype(np.float64)
+    unknown = R12 < 0
+    known = R12[~unknown]
+    R12 = (R12 - known.min()) / (known.max() - known.min())
+    hide = np.logical_and(np.random.RandomState(0).random_sample(R12.shape) > 0.9, ~unknown)
+    mask = np.logical_or(unknown, hide)
+    filled = R12.copy()
+    filled[mask] = R12[~mask].mean()                      # Relation.filled() with fill_value='mean'
+    R23 = np.zeros((n_m, n_g))
+    R23[z["g_m"], z["g_g"]] = 1.
+    R24 = np.zeros((n_m, n_a))
+    R24[z["a_m"], z["a_a"]] = 1.
+    ranks = {"User": max(int(.05 * n_u), 5), "Movie": max(int(.05 * n_m), 5), "Genre": max(int(.05 * n_g), 5),
+             "Actor": max(int(.05 * n_a), 5)}
+    return dict(algo="dfmc", types=["User", "Movie", "Genre", "Actor"], ranks=ranks,
+                R={("User", "Movie"): [filled], ("Movie", "Genre"): [R23], ("Movie", "Actor"): [R24]},
+                M={("User", "Movie"): [mask], ("Movie", "Genre"): [None], ("Movie", "Actor"): [None]},
+                Theta={}, init_type="random_vcol", seed=0, max_iter=30, truth=R12, hidden=hide)

@@ -244,3 +244,28 @@ def test_transform_on_tensor_core_path_against_oracle():
                                dtype="float32", storage="bfloat16", split_terms=2)
     assert got.shape == (n_new, k)
     assert rel_fro(ref, got) < 1e-3
+
+
+def test_movielens_completion_config_against_oracle():
+    """BASELINE config C3: Dfmc on the movielens graph (706 x 1000 ratings, 95.5 % masked; 1000 x 20; 1000 x 1000),
+    fp32 engine vs the float64 oracle on identical inputs, mask and seed; plus the completion quality on the
+    hidden ratings must agree."""
+    from skfusion.fusion import solver
+    case = cases.movielens_case()
+    kw = dict(obj_types=case["types"], obj_type2rank=case["ranks"], max_iter=case["max_iter"], init_type=case["init_type"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Go, So = oracle.dfmc(case["R"], case["M"], case["Theta"], random_state=np.random.RandomState(0), **kw)
+        G, S = solver.dfmc(case["R"], case["M"], case["Theta"], random_state=np.random.RandomState(0), dtype="float32", **kw)
+    for t in case["types"]:
+        err = rel_fro(Go[t, t], G[t, t])
+        assert err < 1e-4, "G[%s] relFro=%.3g" % (t, err)
+    for key in So:
+        err = rel_fro(So[key][0], S[key][0])
+        assert err < 1e-3, "S%s relFro=%.3g" % (key, err)
+    hid, truth = case["hidden"], case["truth"]
+
+    def rmse(Gd, Sd):
+        rec = Gd["User", "User"] @ Sd["User", "Movie"][0] @ Gd["Movie", "Movie"].T
+        return float(np.sqrt(np.mean((rec[hid] - truth[hid]) ** 2)))
+    assert abs(rmse(G, S) - rmse(Go, So)) < 1e-5
