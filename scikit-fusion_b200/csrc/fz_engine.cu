@@ -183,7 +183,10 @@ static void copy_in(const void* src, int64_t lds, int sd, int mem, void* dst, in
   }
   const size_t es = dtype_size(sd);
   if (sd == dd) {
-    CUDA_OK(cudaMemcpy2DAsync(dst, ldd * es, src, lds * es, cols * es, rows, cudaMemcpyHostToDevice, st));
+    if (lds == cols && ldd == cols)   // contiguous on both sides: one linear DMA (the 2-D path is slower over PCIe)
+      CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)rows * cols * es, cudaMemcpyHostToDevice, st));
+    else
+      CUDA_OK(cudaMemcpy2DAsync(dst, ldd * es, src, lds * es, cols * es, rows, cudaMemcpyHostToDevice, st));
     return;
   }
   DevBuf stage;

@@ -3,8 +3,11 @@
 Defaults can be changed process-wide (``engine_options.update(dtype='float64')``), per estimator
 (``Dfmf(..., dtype='float64')``) or through the environment:
     SKFUSION_B200_DEVICE, SKFUSION_B200_DTYPE, SKFUSION_B200_STORAGE, SKFUSION_B200_SPLIT_TERMS
-  dtype        compute dtype of factors and streamed products: 'float32' (default) or 'float64'
-               (parity mode: matches the reference's float64 numpy path to ~1e-12)
+  dtype        compute dtype of factors and streamed products: 'auto' (default), 'float32' or 'float64'.
+               'float64' matches the reference's float64 numpy path to ~1e-8 over a whole fit; 'float32' is the
+               fast path (G <= 1e-4..1e-3, S <= 1e-3..5e-3 depending on conditioning).  'auto' takes float64 while
+               the graph is small (<= AUTO_FP64_MAX_ENTRIES relation entries: every dataset the reference ships),
+               where B200's fp64 rate makes exactness free, and float32 beyond -- or whenever storage is bfloat16.
   storage      device dtype of relation matrices: None (= dtype), or 'bfloat16' to take the
                tcgen05 tensor-core path (rank <= 64, fp32 engine)
   split_terms  bf16 terms used to represent a factor on the tensor-core path (1..3)
@@ -13,15 +16,22 @@ import os
 
 engine_options = {
     "device": int(os.environ.get("SKFUSION_B200_DEVICE", "0")),
-    "dtype": os.environ.get("SKFUSION_B200_DTYPE", "float32"),
+    "dtype": os.environ.get("SKFUSION_B200_DTYPE", "auto"),
     "storage": os.environ.get("SKFUSION_B200_STORAGE") or None,
     "split_terms": int(os.environ.get("SKFUSION_B200_SPLIT_TERMS", "2")),
 }
 
 
-def resolve(**overrides):
+AUTO_FP64_MAX_ENTRIES = 50 * 1000 * 1000
+
+
+def resolve(n_entries=None, **overrides):
+    """Effective engine options; ``n_entries`` (total relation + constraint entries) settles dtype='auto'."""
     opts = dict(engine_options)
     for key, val in overrides.items():
         if val is not None:
             opts[key] = val
+    if opts["dtype"] == "auto":
+        small = n_entries is not None and n_entries <= AUTO_FP64_MAX_ENTRIES
+        opts["dtype"] = "float64" if (small and not opts.get("storage")) else "float32"
     return opts

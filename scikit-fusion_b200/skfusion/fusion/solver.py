@@ -105,7 +105,7 @@ class _Problem(object):
 def _fit(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopping, stopping_system, verbose,
          compute_err, callback, random_state, engine_kwargs):
     _configure_logging(verbose)
-    opts = resolve(**engine_kwargs)
+    opts = resolve(n_entries=_count_entries(R, Theta), **engine_kwargs)
     sizes = count_objects(obj_types, R)
     first = {key: _host_view(mats[0]) for key, mats in R.items()} if init_type != "random" else {}
     G0 = initialize(obj_types, sizes, obj_type2rank, first, init_type, random_state)
@@ -169,6 +169,15 @@ def _target_of(stopping):
     return target, 0
 
 
+def _count_entries(*blocks):
+    total = 0
+    for block in blocks:
+        for mats in (block or {}).values():
+            for mat in mats:
+                total += int(mat.shape[0]) * int(mat.shape[1])
+    return total
+
+
 def _host_view(mat):
     if _capi._is_torch_cuda(mat):
         return mat.float().cpu().numpy().astype(np.float64)
@@ -200,7 +209,7 @@ def transform(R_ij, Theta_i, target_obj_type, obj_type2rank, G, S, max_iter=10, 
     _configure_logging(verbose)
     if not isinstance(random_state, np.random.RandomState):
         random_state = np.random.RandomState(random_state)
-    opts = resolve(**engine_kwargs)
+    opts = resolve(n_entries=_count_entries(R_ij, Theta_i), **engine_kwargs)
     tgt = target_obj_type
     n_targets = [mats[0].shape[0 if tgt == ti else 1] for (ti, tj), mats in R_ij.items()]
     if len(set(n_targets)) > 1:
