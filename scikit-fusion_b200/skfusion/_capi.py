@@ -181,6 +181,7 @@ class Engine(object):
         self._keep = []
         self.type_shape = []     # (n, k) per type id
         self.rel_types = []      # (ti, tj) per relation id
+        self.world, self.rank = 1, 0
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -198,6 +199,13 @@ class Engine(object):
     # ---- description
     def set_shard(self, world, rank):
         self._ck(self._L.fz_set_shard(self._h, world, rank))
+        self.world, self.rank = int(world), int(rank)
+
+    def _local_rows(self, t):
+        n = self.type_shape[t][0]
+        m = (n + self.world - 1) // self.world
+        lo = min(n, self.rank * m)
+        return min(n, lo + m) - lo
 
     def add_type(self, n, k):
         tid = self._ck(self._L.fz_add_type(self._h, int(n), int(k)))
@@ -205,6 +213,14 @@ class Engine(object):
         return tid
 
     def add_relation(self, ti, tj, data, storage=None, borrow=False, mask=None):
+        if not (0 <= ti < len(self.type_shape) and 0 <= tj < len(self.type_shape)):
+            raise EngineError("unknown type id %r / %r" % (ti, tj))
+        want = (self._local_rows(ti), self.type_shape[tj][0])
+        if tuple(int(d) for d in data.shape) != want:
+            # the C side reads rows x cols straight from the pointer: a wrong shape must never get there
+            raise ValueError("relation matrix has shape %r but its object types imply %r" % (tuple(data.shape), want))
+        if mask is not None and tuple(int(d) for d in mask.shape) != want:
+            raise ValueError("mask has shape %r but the relation is %r" % (tuple(mask.shape), want))
         keep, ptr, ld, code, mem = _describe(data)
         st = code if storage is None else dtype_code(storage)
         if st == FZ_U8:
@@ -221,10 +237,20 @@ class Engine(object):
         return rid
 
     def set_factor(self, t, G0):
+        if not 0 <= t < len(self.type_shape):
+            raise EngineError("unknown type id %r" % (t,))
+        if tuple(int(d) for d in G0.shape) != self.type_shape[t]:
+            raise ValueError("factor has shape %r, expected %r" % (tuple(G0.shape), self.type_shape[t]))
         keep, ptr, ld, code, mem = _describe(G0)
         self._ck(self._L.fz_set_factor(self._h, t, ptr, ld, code, mem))
 
     def set_backbone(self, rel, S):
+        if not 0 <= rel < len(self.rel_types):
+            raise EngineError("unknown relation id %r" % (rel,))
+        ti, tj = self.rel_types[rel]
+        want = (self.type_shape[ti][1], self.type_shape[tj][1])
+        if tuple(int(d) for d in S.shape) != want:
+            raise ValueError("backbone has shape %r, expected %r" % (tuple(S.shape), want))
         keep, ptr, ld, code, mem = _describe(S)
         self._ck(self._L.fz_set_backbone(self._h, rel, ptr, ld, code, mem))
 

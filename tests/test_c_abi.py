@@ -62,6 +62,11 @@ def test_host_buffer_round_trip_and_errors():
         other.iterate(_capi.FZ_DFMF, 1)
     with pytest.raises(_capi.EngineError, match="unknown type id"):
         other.add_relation(0, 7, R)
+    other.add_type(9, 3)
+    with pytest.raises(ValueError, match="object types imply"):      # shapes are checked before the pointer crosses the ABI
+        other.add_relation(0, 1, R)
+    with pytest.raises(ValueError, match="factor has shape"):
+        other.set_factor(0, np.zeros((5, 2)))
     other.close()
     before = eng.launches
     eng.iterate(_capi.FZ_DFMF, 3)
