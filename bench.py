@@ -107,6 +107,10 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def fused_kernel_active(args):
+    return os.environ.get("FZ_NO_FUSED", "0") != "1" and args.split_terms == 2
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def gpu_arm(args):
     import torch
@@ -197,13 +201,22 @@ def gpu_arm(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     alg_bytes_per_launch = prof_alg / max(1, n_prof)
+    traffic, traffic_note = None, None
+    try:   # dram__bytes_read+write per launch from the committed ncu --set full capture, scaled to this launch size
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if fused_kernel_active(args):
+            traffic = cap["traffic_over_algorithmic"] * alg_bytes_per_launch
+            traffic_note = "ncu capture at n=40960: %.4f x algorithmic bytes (%s), scaled to this launch" % (
+                cap["traffic_over_algorithmic"], "profiles/r01_ncu_traffic.json")
+    except Exception:
+        pass
     avg_ms = prof_ms / max(1, n_prof)
     achieved = alg_bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    fused = os.environ.get("FZ_NO_FUSED", "0") != "1" and args.split_terms == 2
+    fused = fused_kernel_active(args)
     roofline = {"bound": "hbm", "kernel": "umma_fused_kernel (tcgen05/TMA, A and B from one stream of R)" if fused else
                 "umma_skinny_kernel<N,*> (tcgen05/TMA, one product per pass)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src, "launches_timed": n_prof,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "launches_timed": n_prof,
                 "avg_launch_ms": round(avg_ms, 4), "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "streamed_bytes_per_launch": prof_bytes / max(1, n_prof),
                 "kernel_share_of_step": round(prof_ms / max(1e-9, e0.elapsed_time(e1)), 4)}
