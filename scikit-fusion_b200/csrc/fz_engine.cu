@@ -274,6 +274,13 @@ class Engine : public EngineBase {
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   std::vector<cudaEvent_t> ev_rel_;
   bool use_aux_ = true;      // FZ_NO_AUX=1 keeps everything on the caller's stream
+  // CUDA-graph replay of the iteration for launch-bound (small) graphs; FZ_NO_GRAPH=1 disables
+  bool use_graph_ = true;
+  cudaStream_t gstream_ = nullptr;
+  cudaEvent_t ev_gfork_ = nullptr, ev_gjoin_ = nullptr;
+  cudaGraphExec_t graph_exec_[2] = {nullptr, nullptr};
+  int graph_parity_[2] = {-1, -1};
+  int64_t graph_launches_[2] = {0, 0};
   bool fused_ = true;       // single-pass A/B kernel for bf16 relations (needs terms_ == 2); FZ_NO_FUSED=1 disables
   int fused_csplit_ = 0;    // column splits of the fused kernel (0 = automatic); FZ_FUSED_CSPLIT overrides
   bool finalized_ = false;
@@ -296,6 +303,10 @@ class Engine : public EngineBase {
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
     for (auto e : ev_rel_) cudaEventDestroy(e);
+    for (auto g : graph_exec_) if (g) cudaGraphExecDestroy(g);
+    if (gstream_) cudaStreamDestroy(gstream_);
+    if (ev_gfork_) cudaEventDestroy(ev_gfork_);
+    if (ev_gjoin_) cudaEventDestroy(ev_gjoin_);
   }
   int compute_dtype() const override { return kDT; }
 
@@ -475,6 +486,12 @@ class Engine : public EngineBase {
     if (const char* cs = getenv("FZ_FUSED_CSPLIT")) fused_csplit_ = atoi(cs);
     if (terms_ != 2) fused_ = false;
     if (const char* na = getenv("FZ_NO_AUX")) use_aux_ = !(na[0] == '1');
+    if (const char* ng = getenv("FZ_NO_GRAPH")) use_graph_ = !(ng[0] == '1');
+    if (use_graph_) {
+      CUDA_OK(cudaStreamCreateWithFlags(&gstream_, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_gfork_, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_gjoin_, cudaEventDisableTiming));
+    }
     if (use_aux_) {
       CUDA_OK(cudaStreamCreateWithFlags(&aux_, cudaStreamNonBlocking));
       CUDA_OK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
@@ -493,10 +510,58 @@ class Engine : public EngineBase {
   void iterate(int algo, int n_iters, cudaStream_t st) override {
     need_final();
     if (world_ != 1) FZ_THROW(FZ_ERR_INVALID, "fz_iterate is for unsharded handles; use the fz_phase_* calls");
-    for (int it = 0; it < n_iters; ++it) {
-      phase_products(algo, st);
-      phase_update(algo, st);
+    int done = 0;
+    // Small graphs are launch-latency-bound (tens of kernels of a few microseconds each): after one eager
+    // iteration, two iterations (the factor double-buffer has period two) are captured into a CUDA graph and
+    // replayed.  Large graphs gain nothing from it and keep the per-launch profiling hooks.
+    if (use_graph_ && !profile && n_iters >= 5 && graph_worthwhile()) {
+      run_one(algo, st);
+      ++done;
+      const int pairs = (n_iters - done) / 2;
+      if (pairs > 0) {
+        CUDA_OK(cudaEventRecord(ev_gfork_, st));
+        CUDA_OK(cudaStreamWaitEvent(gstream_, ev_gfork_, 0));
+        const int parity = types_[0]->cur;
+        if (graph_exec_[algo] == nullptr || graph_parity_[algo] != parity) {
+          if (graph_exec_[algo]) { cudaGraphExecDestroy(graph_exec_[algo]); graph_exec_[algo] = nullptr; }
+          const int64_t before = launches;
+          cudaGraph_t graph = nullptr;
+          CUDA_OK(cudaStreamBeginCapture(gstream_, cudaStreamCaptureModeThreadLocal));
+          try {
+            run_one(algo, gstream_);
+            run_one(algo, gstream_);
+          } catch (...) {
+            cudaStreamEndCapture(gstream_, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+          }
+          CUDA_OK(cudaStreamEndCapture(gstream_, &graph));
+          cudaError_t ie = cudaGraphInstantiate(&graph_exec_[algo], graph, 0);
+          cudaGraphDestroy(graph);
+          if (ie != cudaSuccess) FZ_THROW(FZ_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+          graph_launches_[algo] = launches - before;
+          launches = before;                      // capture does not execute anything
+          graph_parity_[algo] = parity;
+        }
+        for (int g = 0; g < pairs; ++g) CUDA_OK(cudaGraphLaunch(graph_exec_[algo], gstream_));
+        launches += graph_launches_[algo] * pairs;
+        done += 2 * pairs;
+        CUDA_OK(cudaEventRecord(ev_gjoin_, gstream_));
+        CUDA_OK(cudaStreamWaitEvent(st, ev_gjoin_, 0));
+      }
     }
+    for (; done < n_iters; ++done) run_one(algo, st);
+  }
+
+  void run_one(int algo, cudaStream_t st) {
+    phase_products(algo, st);
+    phase_update(algo, st);
+  }
+  // worth a graph when the relations are small enough that launch latency, not bandwidth, sets the pace
+  bool graph_worthwhile() const {
+    double entries = 0.0;
+    for (auto& r : rels_) entries += (double)r->rows_loc * (double)r->cols;
+    return entries <= 6.4e7;
   }
 
   void phase_products(int algo, cudaStream_t st) override {
