@@ -11,7 +11,7 @@ pair i<j, n objects per type, rank 64, relations stored in bf16 and generated on
 counter-based generator (identical numbers for every sharding).  The same fixed graph is used at every N
 (strong scaling): type rows are sharded over the ranks, one process per GPU, NCCL for the three exchanges.
 Default n = 81920: the largest power-of-two-ish size whose 10 relations (134 GB) fit one 180 GB B200;
-BASELINE configs[3]'s n=100k (200 GB) needs >= 2 GPUs and can be requested with --n 100000 --gpus >= 2.
+BASELINE configs[3]'s n=100k (200 GB) needs >= 2 GPUs and can be requested with --size 100000 --gpus >= 2.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -36,7 +36,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=0, help="objects per type (0 = 81920, shrunk if HBM is short)")
+    # (not "--n": torch.distributed.run's own parser treats it as an ambiguous abbreviation of --nnodes / --nproc-per-node)
+    ap.add_argument("--size", dest="n", type=int, default=0, help="objects per type (0 = 81920, shrunk if HBM is short)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--split-terms", type=int, default=2)
     ap.add_argument("--cpu-n", type=int, default=4096, help="objects per type of the bounded CPU sample")
