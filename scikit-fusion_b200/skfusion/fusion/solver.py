@@ -250,12 +250,28 @@ def transform(R_ij, Theta_i, target_obj_type, obj_type2rank, G, S, max_iter=10, 
         for rid, key, l in rel_of:
             prob.engine.set_backbone(rid, S[key][l])
         prob.engine.transform_prepare(prob.type_id[id(tgt)])
-        if callback is None:
+        if stopping_system:
+            compute_err = True
+        if callback is None and not compute_err:
             prob.engine.transform_iterate(max_iter)
         else:
+            # per-iteration mode: error tracking / early stopping / callback as in _dfmf.py:367-453
+            err_system, history = (None, None), []
             for it in range(max_iter):
+                if it > 1 and stopping_system and err_system[1] - err_system[0] < stopping_system:
+                    log.info("Early stopping: matrix system change < %5.4f" % stopping_system)
+                    break
                 prob.engine.transform_iterate(1)
-                callback(prob.engine.get_factor(prob.type_id[id(tgt)]), it)
+                if compute_err:
+                    total, _ = prob.engine.objective(len(rel_of))
+                    log.info("Error (objective function value): %5.4f" % total)
+                    history.append(total)
+                    if stopping_system:
+                        err_system = (total, err_system[0])
+                if callback is not None:
+                    callback(prob.engine.get_factor(prob.type_id[id(tgt)]), it)
+            if compute_err and history:
+                log.info("Violations of optimization objective: %d/%d " % (int(np.sum(np.diff(history) > 0)), len(history)))
         return prob.engine.get_factor(prob.type_id[id(tgt)])
     finally:
         prob.close()

@@ -272,3 +272,26 @@ def test_movielens_completion_config_against_oracle(dtype, tol_g, tol_s):
         rec = Gd["User", "User"] @ Sd["User", "Movie"][0] @ Gd["Movie", "Movie"].T
         return float(np.sqrt(np.mean((rec[hid] - truth[hid]) ** 2)))
     assert abs(rmse(G, S) - rmse(Go, So)) < 1e-4
+
+
+def test_transform_error_tracking_and_early_stop_match_oracle():
+    """compute_err / stopping_system of transform(): objective history and the stopping iteration (_dfmf.py:368-450)."""
+    from skfusion.fusion import solver
+    case = cases.transform_cases()["project_rows"]
+    fit = cases.fit_cases()[case["fit"]]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Go, So = oracle.dfmf(fit["R"], {}, fit["types"], fit["ranks"], max_iter=15, init_type="random", random_state=np.random.RandomState(0))
+    tags = {t: cases.Tag(t) for t in fit["types"]}
+    G = {(tags[t], tags[t]): Go[t, t] for t in fit["types"]}
+    S = {(tags[a], tags[b]): v for (a, b), v in So.items()}
+    R_new = {(tags[a], tags[b]): m for (a, b), m in case["R_new"].items()}
+    rk = {tags[t]: r for t, r in fit["ranks"].items()}
+    hist, n_o, n_g = [], [], []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        oracle.transform(R_new, {}, tags["t1"], rk, G, S, max_iter=60, init_type="random", random_state=np.random.RandomState(1),
+                         stopping_system=1e-3, history=hist, callback=lambda g, it: n_o.append(it))
+        solver.transform(R_new, {}, tags["t1"], rk, G, S, max_iter=60, init_type="random", random_state=np.random.RandomState(1),
+                         stopping_system=1e-3, callback=lambda g, it: n_g.append(it), dtype="float64")
+    assert n_o == n_g and 2 < len(n_o) < 60
