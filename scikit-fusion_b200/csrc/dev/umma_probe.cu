@@ -245,32 +245,6 @@ static void bench_fused(int n, int skip_flush) {
   cudaFree(dX); cudaFree(dG); cudaFree(dA); cudaFree(dB);
 }
 
-// v1 kernel on an L2-resident matrix: the SM-side (smem / tensor) throughput limit without HBM in the way
-static void bench_l2_resident() {
-  const int rows = 8192, cols = 4096, N = 128, k = 64;   // 64 MB of bf16: stays in the 126 MB L2
-  __nv_bfloat16 *dX, *dG; float* dC;
-  CK(cudaMalloc(&dX, (size_t)rows * cols * 2)); CK(cudaMalloc(&dG, (size_t)cols * N * 2)); CK(cudaMalloc(&dC, (size_t)rows * k * 4));
-  CK(cudaMemset(dX, 0x3c, (size_t)rows * cols * 2)); CK(cudaMemset(dG, 0x3c, (size_t)cols * N * 2));
-  CUtensorMap tx, tg; std::string err;
-  bool ok = make_tmap_bf16_2d(&tx, dX, rows, cols, cols, 64, 128, &err) && make_tmap_bf16_2d(&tg, dG, cols, N, N, 64, 64, &err);
-  if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
-  SkinnyParams p;
-  p.C = dC; p.ldc = k; p.g_row0 = 0; p.M = rows; p.K = cols; p.k = k; p.kp = 64; p.terms = 2;
-  const int ksplit = 4;
-  p.k_per_split = cols / ksplit; p.atomic = 1;
-  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  for (int w = 0; w < 3; ++w) dispatch(N, false, tx, tg, p, ksplit, 0);
-  CK(cudaDeviceSynchronize());
-  const int reps = 20;
-  CK(cudaEventRecord(e0));
-  for (int r = 0; r < reps; ++r) dispatch(N, false, tx, tg, p, ksplit, 0);
-  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
-  float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
-  printf("bench L2-resident (64 MB, v1 kernel N=128, ksplit=4): %.4f ms  %.1f GB/s from L2\n", ms,
-         (double)rows * cols * 2 / 1e9 / (ms * 1e-3));
-  cudaFree(dX); cudaFree(dG); cudaFree(dC);
-}
-
 int main(int argc, char** argv) {
   int nbench = argc > 1 ? atoi(argv[1]) : 32768;
   int fails = 0;
@@ -295,11 +269,11 @@ int main(int argc, char** argv) {
   fails += run_fused_case(777, 3001, 64, 64, 1);
   printf("correctness: %d failing cases\n", fails);
   if (nbench > 0) {
-    bench_l2_resident();
-    for (int mode : {0, 8, 1, 7}) bench_fused(nbench, mode);
-    return fails ? 1 : 0;
-    for (int trans = 0; trans < 2; ++trans)
-      for (int terms = 1; terms <= 2; ++terms) bench(nbench, terms, trans);
+    for (int mode : {0, 8, 1, 7}) bench_fused(nbench, mode);           // fused kernel: flush variants / component probes
+    if (argc > 2) {                                                     // any second argument: also the two-pass kernels
+      for (int trans = 0; trans < 2; ++trans)
+        for (int terms = 1; terms <= 2; ++terms) bench(nbench, terms, trans);
+    }
   }
   return fails ? 1 : 0;
 }
