@@ -43,9 +43,10 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=4096, help="objects per type of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "readme3", "dicty"],
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "readme3", "dicty", "transform"],
                     help="synthetic = the contract workload; readme3 / dicty = the small BASELINE configs C1 / C2 "
-                         "(latency-bound; informational line, N=1 only)")
+                         "(latency-bound; informational line, N=1 only); transform = config C5 (project 10 000 new "
+                         "rows of type 0 against a 100 000-object model, 4 relations; informational line, N=1 only)")
     return ap.parse_args()
 
 
@@ -368,8 +369,118 @@ def small_workload(args):
                       "note": "latency-bound: no roofline claim (SURVEY.md 8d)"}))
 
 
+def transform_workload(args):
+    """BASELINE config C5: project n_new = 10 000 new objects of type 0 into a fitted space of four
+    other types with n = 100 000 objects each (R_new,0j: 10k x 100k bf16, 8 GB in total), rank 64, init 'random',
+    100 iterations.  The model (G_j, S_0j) is synthetic: timing does not depend on its values.  The engine computes the
+    loop-invariant R_new (G_j S^T) once (one tensor-core pass over R_new) and then iterates on n_new x k operands;
+    the reference recomputes that product every iteration (_dfmf.py:392-405).  CPU leg: the oracle's transform on a
+    bounded sample (1 000 x 10 000 per relation), scaled by the n_new * n product."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fusion_oracle as oracle
+    from skfusion import _capi
+    n_new, n, iters = (10000, args.n if args.n > 0 else 100000, 100)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    rs = np.random.RandomState(0)
+    eng = _capi.Engine(0, "float32")
+    eng.set_split_terms(args.split_terms)
+    tgt = eng.add_type(n_new, RANK)
+    others = [eng.add_type(n, RANK) for _ in range(4)]
+    rels, keep = [], []
+    for j, tj in enumerate(others):
+        t = torch.empty((n_new, n), dtype=torch.bfloat16, device=dev)
+        _capi.fill_uniform(t, SEED0 + 1 + j, stream=st)
+        keep.append(t)
+        rels.append(eng.add_relation(tgt, tj, t, storage="bfloat16", borrow=True))
+    G_new0 = rs.rand(n_new, RANK).astype(np.float32)
+    eng.set_factor(tgt, G_new0)
+    for tj in others:
+        eng.set_factor(tj, rs.rand(n, RANK).astype(np.float32))
+    eng.finalize()
+    for r in rels:
+        eng.set_backbone(r, rs.rand(RANK, RANK) / RANK)
+
+    def one_call():
+        eng.set_factor(tgt, G_new0)
+        torch.cuda.synchronize(dev)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        eng.transform_prepare(tgt, st)
+        e1.record()
+        eng.transform_iterate(iters, st)
+        e2.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), e1.elapsed_time(e2)
+
+    for _ in range(max(3, args.warmup)):
+        one_call()
+    l0 = eng.launches
+    eng.profile(True)
+    runs = [one_call() for _ in range(5)]
+    # transform needs ONE product per relation, so the algorithmic bytes of a launch are the bytes it streams
+    n_prof, prof_ms, prof_alg, _ = eng.profile_read()
+    eng.profile(False)
+    launches = (eng.launches - l0) // 5
+    prep_ms = float(np.median([r[0] for r in runs]))
+    iter_ms = float(np.median([r[1] for r in runs]))
+    total_ms = prep_ms + iter_ms
+    G_out = eng.get_factor(tgt)
+    assert np.isfinite(G_out).all()
+    eng.close()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = prof_alg / max(1e-9, prof_ms * 1e-3) / 1e9
+
+    # CPU leg: oracle transform, float64, reference evaluation order (recomputes R_new (G_j S^T) per iteration)
+    cn_new, cn, cit = 1000, 10000, 5
+    tags = [oracle_tag(i) for i in range(5)]
+    Rc = {(tags[0], tags[1 + j]): [oracle.bf16_round(oracle.hashed_uniform(SEED0 + 1 + j, cn_new, cn))] for j in range(4)}
+    Gc = {(tags[1 + j], tags[1 + j]): rs.rand(cn, RANK) for j in range(4)}
+    Sc = {(tags[0], tags[1 + j]): [rs.rand(RANK, RANK) / RANK] for j in range(4)}
+    rk = {t: RANK for t in tags}
+    stamps = []
+    oracle.transform(Rc, {}, tags[0], rk, Gc, Sc, max_iter=cit + 1, init_type="random", random_state=np.random.RandomState(1),
+                     callback=lambda g, it: stamps.append(time.perf_counter()))
+    cpu_it_s = float(np.median(np.diff(stamps)))
+    cpu_it_s_full = cpu_it_s * (float(n_new) * n) / (float(cn_new) * cn)
+    print(json.dumps({
+        "metric": "transform rows*iterations/sec, BASELINE config C5", "value": round(n_new * iters / (total_ms * 1e-3), 1),
+        "unit": "rows*it/s", "n_gpus": 1, "iterations": iters, "wall_ms": round(total_ms, 3),
+        "prepare_ms": round(prep_ms, 3), "iterate_ms": round(iter_ms, 3), "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "transform: %d new rows of type 0 x 4 relations %d x %d bf16 (%.1f GB), rank 64, %d-term bf16 "
+                               "split of the frozen operand G_j S^T, %d iterations" % (n_new, n_new, n, 4.0 * n_new * n * 2 / 1e9,
+                                                                                     args.split_terms, iters)},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "umma_skinny_kernel<N,false> (R_new (G_j S^T), once per call)",
+                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "launches_timed": n_prof},
+        "cpu_baseline": {"value": round(n_new / cpu_it_s_full, 1), "unit": "rows*it/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "oracle transform (float64 numpy, recomputes the relation products every iteration) on "
+                                   "%d x %d per relation: %.3f s/it, scaled by n_new*n to %.1f s/it" % (cn_new, cn, cpu_it_s, cpu_it_s_full)},
+    }))
+
+
+class oracle_tag(object):
+    """Object-type stand-in with identity semantics (transform matches types with ``is``)."""
+
+    def __init__(self, i):
+        self.i = i
+
+    def __repr__(self):
+        return "type%d" % self.i
+
+
 def main():
     args = parse()
+    if args.workload == "transform":
+        transform_workload(args)
+        return
     if args.workload != "synthetic":
         small_workload(args)
         return

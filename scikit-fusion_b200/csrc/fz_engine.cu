@@ -61,8 +61,12 @@ struct DevBuf {
     bytes = 0;
   }
   void alloc(size_t n, bool zero = true) {
-    release();
     if (n == 0) n = 16;
+    if (p && bytes == n) {   // same size again (e.g. a second fz_transform_prepare): keep the allocation
+      if (zero) CUDA_OK(cudaMemset(p, 0, n));
+      return;
+    }
+    release();
     cudaError_t e = cudaMalloc(&p, n);
     if (e != cudaSuccess) {
       p = nullptr;
