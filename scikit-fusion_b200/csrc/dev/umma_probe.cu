@@ -9,6 +9,7 @@
 #include <string>
 #include "../umma_skinny.cuh"
 #include "../umma_fused.cuh"
+#include "../umma_fused_t.cuh"
 #include "../tmap.h"
 
 #define CK(x)                                                                          \
@@ -22,6 +23,14 @@
 
 using namespace fz;
 
+static double g_sustain_s = 0.0;   // > 0: time the kernels in a loop of this many seconds (power-capped regime)
+__global__ void fill_random_bf16(__nv_bfloat16* x, size_t n, uint32_t seed, float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + seed;
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    x[i] = __float2bfloat16_rn((h >> 8) * (1.0f / 16777216.0f) * scale);
+  }
+}
 static uint32_t rng_state = 12345u;
 static float frand() {
   rng_state = rng_state * 1664525u + 1013904223u;
@@ -216,6 +225,10 @@ static void bench_fused(int n, int skip_flush) {
   CK(cudaMalloc(&dX, elems * 2)); CK(cudaMalloc(&dG, (size_t)n * N * 2));
   CK(cudaMalloc(&dA, (size_t)n * k * 4)); CK(cudaMalloc(&dB, (size_t)n * k * 4));
   CK(cudaMemset(dX, 0x3c, elems * 2)); CK(cudaMemset(dG, 0x3c, (size_t)n * N * 2));
+  if (g_sustain_s > 0) {   // random operands: switching activity (power) like real data
+    fill_random_bf16<<<1184, 256>>>(dX, elems, 1u, 1.0f);
+    fill_random_bf16<<<1184, 256>>>(dG, (size_t)n * N, 2u, 1.0f);
+  }
   CUtensorMap tr, tg, tg64, tb; std::string err;
   bool ok = make_tmap_bf16_2d(&tr, dX, n, n, n, 64, 128, &err) && make_tmap_bf16_2d(&tg, dG, n, N, N, 64, 128, &err) &&
             make_tmap_bf16_2d(&tg64, dG, n, N, N, 64, 64, &err) && make_tmap_f32_2d(&tb, dB, n, k, k, 32, 32, &err);
@@ -234,18 +247,220 @@ static void bench_fused(int n, int skip_flush) {
     for (int w = 0; w < 2; ++w) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, p);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    const int reps = 40;
+    int reps = 40;
+    float ms;
+    if (g_sustain_s > 0) {
+      // warm into the power-capped regime for half the time, then measure the second half
+      reps = (int)(g_sustain_s * 0.5 / 0.6e-3);
+      for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, p);
+    }
     CK(cudaEventRecord(e0));
     for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, p);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
-    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
-    printf("bench FUSED%s n=%d csplit=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", skip_flush == 0 ? " (tma flush)" : skip_flush == 8 ? " (red flush)" : (skip_flush == 1 ? " (probe: no RED)" : (skip_flush == 2 ? " (probe: no B MMA)" : (skip_flush == 4 ? " (probe: no A MMA)" : (skip_flush == 3 ? " (probe: no RED, no B MMA)" : " (probe: TMA only)")))), n, splits, grid.x, grid.y,
+    CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+    printf("bench FUSED%s n=%d csplit=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", skip_flush == 0 ? " (tma flush)" : skip_flush == 8 ? " (red flush)" : (skip_flush == 1 ? " (probe: no RED)" : (skip_flush == 2 ? " (probe: no B MMA)" : (skip_flush == 4 ? " (probe: no A MMA)" : (skip_flush == 3 ? " (probe: no RED, no B MMA)" : (skip_flush == 6 ? " (probe: no MMA, flush on)" : " (probe: TMA only)"))))), n, splits, grid.x, grid.y,
            ms, elems * 2.0 / 1e9 / (ms * 1e-3), 2.0 * 2.0 * elems * N / (ms * 1e-3) / 1e12);
   }
   cudaFree(dX); cudaFree(dG); cudaFree(dA); cudaFree(dB);
 }
 
+
+// ---- v4 (transposed accumulators, TMEM-resident factor operand): same contract, operands in the GsT form
+static inline int gst_row(int term, int q) { return 32 * (q >> 4) + 16 * term + (q & 15); }
+
+static bool make_tmap_generic(CUtensorMap* out, CUtensorMapDataType dt, int esz, const void* base, uint64_t rows, uint64_t cols,
+                              uint64_t ld, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw, std::string* err) {
+  PFN_encodeTiled enc = get_encode_tiled(err);
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * esz};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { if (err) *err = "encode failed " + std::to_string((int)r); return false; }
+  return true;
+}
+
+static int run_fused_t_case(int rows, int cols, int ka, int kb, int csplit, int tma_flush, int variant, int gi_row0 = 0,
+                            bool device_split = false) {
+  const int ld = (cols + 7) / 8 * 8;
+  const long long ldtj = ((cols + 255) / 256) * 256 + 256, ldti = ((gi_row0 + rows + 255) / 256) * 256 + 256;
+  std::vector<__nv_bfloat16> hX((size_t)rows * ld), hGjT((size_t)128 * ldtj, __float2bfloat16(0.f)), hGiT((size_t)128 * ldti, __float2bfloat16(0.f));
+  std::vector<float> fX((size_t)rows * ld), gj((size_t)cols * 64, 0.f), gi((size_t)rows * 64, 0.f);   // hi + lo as the kernel sees them
+  std::vector<float> Gj32((size_t)cols * 64, 0.f), Gi32((size_t)(gi_row0 + rows) * 64, 0.f);
+  for (size_t i = 0; i < hX.size(); ++i) { hX[i] = __float2bfloat16(frand() - 0.3f); fX[i] = __bfloat162float(hX[i]); }
+  auto fill = [&](std::vector<__nv_bfloat16>& hT, long long ldt, std::vector<float>& sum, std::vector<float>& g32, int n, int k, int off) {
+    for (int r = 0; r < n; ++r)
+      for (int q = 0; q < k; ++q) {
+        const float v = frand() - 0.5f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        hT[(size_t)gst_row(0, q) * ldt + off + r] = hi;
+        hT[(size_t)gst_row(1, q) * ldt + off + r] = lo;
+        sum[(size_t)r * 64 + q] = __bfloat162float(hi) + __bfloat162float(lo);
+        g32[(size_t)(off + r) * 64 + q] = v;
+      }
+  };
+  fill(hGjT, ldtj, gj, Gj32, cols, ka, 0);
+  fill(hGiT, ldti, gi, Gi32, rows, kb, gi_row0);
+  __nv_bfloat16 *dX, *dGjT, *dGiT; float *dA, *dB;
+  CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dGjT, hGjT.size() * 2)); CK(cudaMalloc(&dGiT, hGiT.size() * 2));
+  CK(cudaMalloc(&dA, (size_t)rows * ka * 4)); CK(cudaMalloc(&dB, (size_t)cols * kb * 4));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  if (device_split) {
+    // operand forms built by split_factor_t from fp32 factors (k columns, ld = 64)
+    float *dGj32, *dGi32;
+    CK(cudaMalloc(&dGj32, Gj32.size() * 4)); CK(cudaMalloc(&dGi32, Gi32.size() * 4));
+    CK(cudaMemcpy(dGj32, Gj32.data(), Gj32.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dGi32, Gi32.data(), Gi32.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dGjT, 0, hGjT.size() * 2)); CK(cudaMemset(dGiT, 0, hGiT.size() * 2));
+    split_factor_t<float><<<(cols + 63) / 64, 256>>>(dGj32, 64, dGjT, ldtj, cols, ldtj, ka);
+    split_factor_t<float><<<(gi_row0 + rows + 63) / 64, 256>>>(dGi32, 64, dGiT, ldti, gi_row0 + rows, ldti, kb);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<__nv_bfloat16> chk(hGjT.size());
+    CK(cudaMemcpy(chk.data(), dGjT, chk.size() * 2, cudaMemcpyDeviceToHost));
+    size_t bad = 0;
+    for (size_t i = 0; i < chk.size(); ++i) bad += (__bfloat16_as_ushort(chk[i]) != __bfloat16_as_ushort(hGjT[i]));
+    std::vector<__nv_bfloat16> chk2(hGiT.size());
+    CK(cudaMemcpy(chk2.data(), dGiT, chk2.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < chk2.size(); ++i) {
+      // rows below gi_row0 hold other random data on the device side (Gi32 rows < gi_row0 are zero here) -> identical anyway
+      bad += (__bfloat16_as_ushort(chk2[i]) != __bfloat16_as_ushort(hGiT[i]));
+    }
+    printf("split_factor_t vs host operand form: %zu mismatching elements %s\n", bad, bad ? "FAIL" : "OK");
+    cudaFree(dGj32); cudaFree(dGi32);
+    if (bad) return 1;
+  } else {
+    CK(cudaMemcpy(dGjT, hGjT.data(), hGjT.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dGiT, hGiT.data(), hGiT.size() * 2, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemset(dA, 0, (size_t)rows * ka * 4)); CK(cudaMemset(dB, 0, (size_t)cols * kb * 4));
+  CUtensorMap tr, tgj, tb; std::string err;
+  if (kb % 4 != 0) tma_flush = 0;
+  bool ok = make_tmap_bf16_2d(&tr, dX, rows, cols, ld, 64, 256, &err) && make_tmap_bf16_2d(&tgj, dGjT, 128, ldtj, ldtj, 64, 128, &err);
+  if (ok && tma_flush) ok = make_tmap_generic(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dB, cols, kb, kb, 16, 64, CU_TENSOR_MAP_SWIZZLE_NONE, &err);
+  if (!tma_flush) tb = tr;
+  if (!ok) { printf("fusedT rows=%d cols=%d ka=%d kb=%d: tmap error: %s  FAIL\n", rows, cols, ka, kb, err.c_str()); return 1; }
+  FusedTParams p;
+  p.A = dA; p.B = dB; p.lda = ka; p.ldb = kb; p.GiT = dGiT; p.ldt = ldti; p.n_rows = rows; p.n_cols = cols; p.k_a = ka; p.k_b = kb;
+  p.gi_row0 = gi_row0; p.tma_flush = tma_flush; p.variant = variant;
+  const int tiles = (cols + 127) / 128;
+  p.tiles_per_split = (tiles + csplit - 1) / csplit;
+  const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.a_atomic = splits > 1;
+  CK(cudaFuncSetAttribute(umma_fused_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes));
+  dim3 grid((rows + 255) / 256, splits);
+  umma_fused_t_kernel<<<grid, kFtThreads, kFtSmemBytes>>>(tr, tgj, tb, p);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hA((size_t)rows * ka), hB((size_t)cols * kb);
+  CK(cudaMemcpy(hA.data(), dA, hA.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hB.data(), dB, hB.size() * 4, cudaMemcpyDeviceToHost));
+  double ma = 0, ea = 0, mb = 0, eb = 0;
+  for (int m = 0; m < rows; ++m)
+    for (int q = 0; q < ka; ++q) {
+      double s = 0;
+      for (int c = 0; c < cols; ++c) s += (double)fX[(size_t)m * ld + c] * (double)gj[(size_t)c * 64 + q];
+      ma = fmax(ma, fabs(s)); ea = fmax(ea, fabs(s - hA[(size_t)m * ka + q]));
+    }
+  for (int c = 0; c < cols; ++c)
+    for (int q = 0; q < kb; ++q) {
+      double s = 0;
+      for (int r = 0; r < rows; ++r) s += (double)fX[(size_t)r * ld + c] * (double)gi[(size_t)r * 64 + q];
+      mb = fmax(mb, fabs(s)); eb = fmax(eb, fabs(s - hB[(size_t)c * kb + q]));
+    }
+  const bool good = ea / ma < 2e-5 && eb / mb < 2e-5;
+  printf("fusedT rows=%d cols=%d ka=%d kb=%d csplit=%d flush=%s variant=%d gi_row0=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka,
+         kb, splits, tma_flush ? "tma" : "red", variant, gi_row0, ea / ma, eb / mb, good ? "OK" : "FAIL");
+  cudaFree(dX); cudaFree(dGjT); cudaFree(dGiT); cudaFree(dA); cudaFree(dB);
+  return good ? 0 : 1;
+}
+
+static void bench_fused_t(int n, int variant, int csplit) {
+  const int k = 64;
+  size_t elems = (size_t)n * n;
+  const long long ldt = ((n + 255) / 256) * 256 + 256;
+  __nv_bfloat16 *dX, *dGT; float *dA, *dB;
+  CK(cudaMalloc(&dX, elems * 2)); CK(cudaMalloc(&dGT, (size_t)128 * ldt * 2));
+  CK(cudaMalloc(&dA, (size_t)n * k * 4)); CK(cudaMalloc(&dB, (size_t)n * k * 4));
+  CK(cudaMemset(dX, 0x3c, elems * 2)); CK(cudaMemset(dGT, 0x3c, (size_t)128 * ldt * 2));
+  if (g_sustain_s > 0) {
+    fill_random_bf16<<<1184, 256>>>(dX, elems, 1u, 1.0f);
+    fill_random_bf16<<<1184, 256>>>(dGT, (size_t)128 * ldt, 2u, 1.0f);
+  }
+  CUtensorMap tr, tg, tb; std::string err;
+  bool ok = make_tmap_bf16_2d(&tr, dX, n, n, n, 64, 256, &err) && make_tmap_bf16_2d(&tg, dGT, 128, ldt, ldt, 64, 128, &err) &&
+            make_tmap_generic(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dB, n, k, k, 16, 64, CU_TENSOR_MAP_SWIZZLE_NONE, &err);
+  if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
+  CK(cudaFuncSetAttribute(umma_fused_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes));
+  FusedTParams p;
+  p.A = dA; p.B = dB; p.lda = k; p.ldb = k; p.GiT = dGT; p.ldt = ldt; p.n_rows = n; p.n_cols = n; p.k_a = k; p.k_b = k; p.gi_row0 = 0;
+  p.tma_flush = 1; p.variant = variant;
+  const int tiles = (n + 127) / 128;
+  p.tiles_per_split = (tiles + csplit - 1) / csplit;
+  const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.a_atomic = splits > 1;
+  dim3 grid((n + 255) / 256, splits);
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int w = 0; w < 2; ++w) umma_fused_t_kernel<<<grid, kFtThreads, kFtSmemBytes>>>(tr, tg, tb, p);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  int reps = 40;
+  float ms;
+  if (g_sustain_s > 0) {
+    reps = (int)(g_sustain_s * 0.5 / 0.6e-3);
+    for (int r = 0; r < reps; ++r) umma_fused_t_kernel<<<grid, kFtThreads, kFtSmemBytes>>>(tr, tg, tb, p);
+  }
+  CK(cudaEventRecord(e0));
+  for (int r = 0; r < reps; ++r) umma_fused_t_kernel<<<grid, kFtThreads, kFtSmemBytes>>>(tr, tg, tb, p);
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+  printf("bench FUSED-T variant=%d n=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", variant, n, grid.x, grid.y,
+         ms, elems * 2.0 / 1e9 / (ms * 1e-3), 2.0 * 2.0 * elems * 128 / (ms * 1e-3) / 1e12);
+  cudaFree(dX); cudaFree(dGT); cudaFree(dA); cudaFree(dB);
+}
+
+static int main_fused_t(int variant, int nbench) {
+  int fails = 0;
+  fails += run_fused_t_case(256, 64, 64, 64, 1, 1, variant);
+  fails += run_fused_t_case(256, 256, 64, 64, 1, 1, variant);
+  fails += run_fused_t_case(512, 384, 64, 64, 1, 1, variant);
+  fails += run_fused_t_case(1000, 520, 64, 40, 1, 1, variant);
+  fails += run_fused_t_case(520, 1000, 50, 64, 3, 1, variant);
+  fails += run_fused_t_case(2048, 4096, 64, 64, 4, 1, variant);
+  fails += run_fused_t_case(1000, 520, 64, 40, 1, 0, variant);
+  fails += run_fused_t_case(3000, 2100, 33, 36, 2, 1, variant);
+  fails += run_fused_t_case(777, 3001, 64, 64, 1, 1, variant);
+  fails += run_fused_t_case(777, 1001, 64, 64, 2, 1, variant, 1024);     // sharded: factor rows offset, 16-byte aligned
+  fails += run_fused_t_case(500, 1001, 64, 48, 1, 1, variant, 12500);    // sharded: offset not a multiple of 8 (scalar preload)
+  fails += run_fused_t_case(1000, 520, 64, 40, 1, 1, variant, 0, true);  // operand forms from split_factor_t
+  fails += run_fused_t_case(777, 1001, 20, 64, 2, 1, variant, 1024, true);
+  fails += run_fused_t_case(130, 77, 7, 12, 1, 1, variant);              // boxes larger than the tensors
+  fails += run_fused_t_case(300, 40, 64, 8, 1, 1, variant);
+  printf("fusedT correctness (variant %d): %d failing cases\n", variant, fails);
+  if (nbench > 0) {
+    bench_fused_t(nbench, variant, 1);
+    bench_fused_t(nbench, variant | 16, 1);   // no staggered sweep
+    bench_fused_t(nbench, variant | 8, 1);    // no flush
+    bench_fused_t(nbench, variant | 2, 1);    // no B^T-product
+    bench_fused_t(nbench, variant | 4, 1);    // no A^T-product
+    bench_fused_t(nbench, variant | 14, 1);   // TMA only
+  }
+  return fails ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 's') {   // sustained (power-capped) component study:  s <n> <seconds>
+    const int n = argc > 2 ? atoi(argv[2]) : 37888;
+    g_sustain_s = argc > 3 ? atof(argv[3]) : 4.0;
+    printf("sustained mode: %.1f s per configuration (second half timed)\n", g_sustain_s);
+    for (int mode : {0, 2, 4, 6, 7}) bench_fused(n, mode);            // v3: full, no B MMA, no A MMA, no MMA, TMA only
+    for (int v : {0, 2, 4, 6, 14}) bench_fused_t(n, v, 1);            // v4: same
+    return 0;
+  }
+  if (argc > 1 && argv[1][0] == 't') return main_fused_t(argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atoi(argv[3]) : 0);
   int nbench = argc > 1 ? atoi(argv[1]) : 32768;
   int fails = 0;
   for (int trans = 0; trans < 2; ++trans)

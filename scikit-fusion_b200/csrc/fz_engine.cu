@@ -26,6 +26,7 @@
 #include "fz_kernels.cuh"
 #include "tmap.h"
 #include "umma_fused.cuh"
+#include "umma_fused_t.cuh"
 #include "umma_skinny.cuh"
 
 namespace fz {
@@ -240,6 +241,9 @@ class Engine : public EngineBase {
     DevBuf Gs;               // bf16 [n_pad][terms*kKp]
     CUtensorMap tmG;         // box {64 cols, 64 rows}   (two-pass kernels)
     CUtensorMap tmG128;      // box {64 cols, 128 rows}  (fused kernel)
+    DevBuf GsT;              // bf16 [128][ldt]: transposed operand form (umma_fused_t.cuh), fused kernel v4
+    int64_t ldt = 0;
+    CUtensorMap tmGT;        // box {64 cols, 128 rows}
     DevBuf gram_part;
     int gram_chunks = 0, gram_rows_per_chunk = 0;
     double* gram_raw = nullptr;  // inside `small`
@@ -267,6 +271,8 @@ class Engine : public EngineBase {
     bool has_backbone = false;
     CUtensorMap tmX, tmXT, tmEs, tmB;
     bool has_tmB = false;
+    CUtensorMap tmX256, tmB16;   // fused kernel v4: relation box {64 cols, 256 rows}; B box {16 cols, 64 rows}, no swizzle
+    bool has_tmB16 = false, v4_ok = false;
   };
 
   int device_;
@@ -287,6 +293,8 @@ class Engine : public EngineBase {
   int64_t graph_launches_[2] = {0, 0};
   bool fused_ = true;       // single-pass A/B kernel for bf16 relations (needs terms_ == 2); FZ_NO_FUSED=1 disables
   int fused_csplit_ = 0;    // column splits of the fused kernel (0 = automatic); FZ_FUSED_CSPLIT overrides
+  int fused_ver_ = 3;       // 3: umma_fused.cuh (row-form accumulators), 4: umma_fused_t.cuh (transposed, TMEM-resident
+                            // factor operand); FZ_FUSED_VER overrides
   bool finalized_ = false;
   bool dfmc_started_ = false;
   std::vector<std::unique_ptr<TypeRec>> types_;
@@ -422,6 +430,8 @@ class Engine : public EngineBase {
     CUDA_OK(cudaGetDeviceProperties(&prop, device_));
     const int sms = prop.multiProcessorCount;
     sm_count_ = sms;
+    if (const char* fv = getenv("FZ_FUSED_VER")) fused_ver_ = atoi(fv);
+    if (fused_ver_ != 3 && fused_ver_ != 4) FZ_THROW(FZ_ERR_INVALID, "FZ_FUSED_VER must be 3 or 4");
     // fp64 all-reduce buffer: [gram_t ...][M_r ...]
     small_count_ = 0;
     for (auto& t : types_) small_count_ += (int64_t)t->k * t->k;
@@ -446,6 +456,14 @@ class Engine : public EngineBase {
       if (!t.thetas.empty()) {
         t.thP.alloc((size_t)t.m_loc * t.k * sizeof(T));
         t.thN.alloc((size_t)t.m_loc * t.k * sizeof(T));
+      }
+      if (t.need_gs && fused_ver_ == 4 && terms_ == 2 && kDT == FZ_F32) {
+        t.ldt = ((t.n_pad + 255) / 256) * 256 + 256;   // a CTA preloads 256 rows from any local row offset
+        t.GsT.alloc((size_t)128 * t.ldt * 2);
+        CUDA_OK(cudaMemset(t.GsT.p, 0, t.GsT.bytes));
+        std::string e;
+        if (!make_tmap_bf16_2d(&t.tmGT, t.GsT.p, 128, (uint64_t)t.ldt, (uint64_t)t.ldt, 64, 128, &e))
+          FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
       }
       if (t.need_gs) {
         t.Gs.alloc((size_t)t.n_pad * terms_ * kKp * 2);
@@ -483,6 +501,14 @@ class Engine : public EngineBase {
         // reduce target of the fused kernel's TMA flush (fp32, box 32 x 32, 128B swizzle)
         if (kDT == FZ_F32 && (Ti.k % 4) == 0 && Ti.k >= 32)
           r.has_tmB = make_tmap_f32_2d(&r.tmB, r.B.p, (uint64_t)Tj.n_pad, (uint64_t)Ti.k, (uint64_t)Ti.k, 32, 32, &e);
+        // v4 boxes are {64, 256} on the relation and {16, 64} on B: relations smaller than a box keep the v3 kernel
+        if (fused_ver_ == 4 && kDT == FZ_F32 && r.rows_loc >= 256 && r.cols >= 64 && Ti.GsT.p != nullptr && Tj.GsT.p != nullptr) {
+          r.v4_ok = make_tmap_2d(&r.tmX256, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols,
+                                 (uint64_t)r.ld, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B, &e);
+          if (r.v4_ok && (Ti.k % 4) == 0 && Ti.k >= 16 && Tj.n_pad >= 64)
+            r.has_tmB16 = make_tmap_2d(&r.tmB16, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, r.B.p, (uint64_t)Tj.n_pad, (uint64_t)Ti.k,
+                                       (uint64_t)Ti.k, 16, 64, CU_TENSOR_MAP_SWIZZLE_NONE, &e);
+        }
       }
     }
     err_acc_.alloc(8);
@@ -858,6 +884,7 @@ class Engine : public EngineBase {
     umma_attr<128, false>(); umma_attr<128, true>();
     umma_attr<192, false>(); umma_attr<192, true>();
     cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes);
+    cudaFuncSetAttribute(umma_fused_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes);
     cudaFuncSetAttribute(pinv_spd, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
     cudaFuncSetAttribute(backbone_chain<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
   }
@@ -868,6 +895,10 @@ class Engine : public EngineBase {
     split_factor<T><<<nblk(t.n_pad * kKp, 256), 256, 0, st>>>(cur(t), t.k, t.Gs.template as<__nv_bfloat16>(), t.n, t.n_pad, t.k, kKp,
                                                                terms_);
     ++launches;
+    if (t.GsT.p != nullptr) {
+      split_factor_t<T><<<nblk(t.n_pad, 64), 256, 0, st>>>(cur(t), t.k, t.GsT.template as<__nv_bfloat16>(), t.ldt, t.n, t.ldt, t.k);
+      ++launches;
+    }
   }
 
   // Gram matrices of the current factors over the local rows (+ bf16 operand form where needed)
@@ -1171,7 +1202,19 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   if (p.a_atomic) CUDA_OK(cudaMemsetAsync(r.A.p, 0, (size_t)r.rows_loc * Tj.k * sizeof(float), st));
   dim3 grid(pairs, splits);
   prof_begin(st);
-  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(r.tmX, Tj.tmG, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX, p);
+  if (fused_ver_ == 4 && r.v4_ok) {
+    FusedTParams q;
+    q.A = p.A; q.B = p.B; q.lda = p.lda; q.ldb = p.ldb;
+    q.GiT = Ti.GsT.template as<__nv_bfloat16>();
+    q.ldt = Ti.ldt;
+    q.n_rows = p.n_rows; q.n_cols = p.n_cols; q.k_a = p.k_a; q.k_b = p.k_b; q.gi_row0 = p.gi_row0;
+    q.tiles_per_split = p.tiles_per_split; q.a_atomic = p.a_atomic;
+    q.tma_flush = r.has_tmB16 ? 1 : 0;
+    q.variant = 0;
+    umma_fused_t_kernel<<<grid, kFtThreads, kFtSmemBytes, st>>>(r.tmX256, Tj.tmGT, r.has_tmB16 ? r.tmB16 : r.tmX256, q);
+  } else {
+    umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(r.tmX, Tj.tmG, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX, p);
+  }
   ++launches;
   prof_end(st, 2.0 * (double)r.rows_loc * (double)r.cols, /*passes=*/1);
   return true;

@@ -101,45 +101,58 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer: relation tiles
-    if (lane == 0) {
-      int it = 0;
-      for (int c = 0; c < n_tiles; ++c) {
-        const int col0 = (tile_begin + c) * kFuTile;
-        for (int t = 0; t < 2; ++t, ++it) {
-          const int s = it % kFuRStages;
-          ptx::mbar_wait(&r_empty[s], ((it / kFuRStages) & 1) ^ 1);
+    // (whole warp, one elected lane issues: under a divergent `if (lane == 0)` ptxas wraps every TMA / tcgen05
+    //  instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop of ~100 cycles, csrc/dev/mma_pace.cu)
+    int it = 0;
+    for (int c = 0; c < n_tiles; ++c) {
+      const int col0 = (tile_begin + c) * kFuTile;
+      for (int t = 0; t < 2; ++t, ++it) {
+        const int s = it % kFuRStages;
+        ptx::mbar_wait(&r_empty[s], ((it / kFuRStages) & 1) ^ 1);
+        if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&r_full[s], kFuTileBytes);
           for (int ch = 0; ch < 2; ++ch)
             ptx::tma_load_2d(r_st + s * kFuTileBytes + ch * 16384, &tmR, &r_full[s], col0 + ch * 64, r0 + t * kFuTile,
                              ptx::kEvictFirst);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 6) {
     // ---------------------------------------------------------------- TMA producer: factor operands
     // (own warp so that a Gs_j half is requested the moment its ring slot frees up, ~1.25 tiles ahead of use,
     //  instead of queueing behind relation tiles that wait for a free stage)
-    if (lane == 0 && n_tiles > 0) {
-      ptx::mbar_expect_tx(gi_full, 2 * kFuTileBytes);            // resident Gs_i tiles of the two row blocks
-      for (int t = 0; t < 2; ++t)
-        for (int ch = 0; ch < 2; ++ch)
-          ptx::tma_load_2d(gi_st + t * kFuTileBytes + ch * 16384, &tmGi, gi_full, ch * 64, p.gi_row0 + r0 + t * kFuTile,
-                           ptx::kEvictLast);
+    if (n_tiles > 0) {
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(gi_full, 2 * kFuTileBytes);          // resident Gs_i tiles of the two row blocks
+        for (int t = 0; t < 2; ++t)
+          for (int ch = 0; ch < 2; ++ch)
+            ptx::tma_load_2d(gi_st + t * kFuTileBytes + ch * 16384, &tmGi, gi_full, ch * 64, p.gi_row0 + r0 + t * kFuTile,
+                             ptx::kEvictLast);
+      }
+      __syncwarp();
       for (int i = 0; i < 2 * n_tiles; ++i) {
         const int col0 = (tile_begin + (i >> 1)) * kFuTile + (i & 1) * 64;
         const int slot = i % kFuGjSlots;
         ptx::mbar_wait(&gj_empty[slot], ((i / kFuGjSlots) & 1) ^ 1);
-        ptx::mbar_expect_tx(&gj_full[slot], kFuHalfBytes);
-        for (int ch = 0; ch < 2; ++ch)
-          ptx::tma_load_2d(gj_st + slot * kFuHalfBytes + ch * 8192, &tmGj, &gj_full[slot], ch * 64, col0, ptx::kEvictLast);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&gj_full[slot], kFuHalfBytes);
+          for (int ch = 0; ch < 2; ++ch)
+            ptx::tma_load_2d(gj_st + slot * kFuHalfBytes + ch * 8192, &tmGj, &gj_full[slot], ch * 64, col0, ptx::kEvictLast);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0 && n_tiles > 0) {
+    // (whole warp converged, one elected lane issues -- see the producer note above: this removes ~100 cycles of
+    //  waterfall-loop overhead per tcgen05.mma, which at 16 MMAs per tile was the kernel's actual bound)
+    if (n_tiles > 0) {
       constexpr uint32_t idesc_a = ptx::idesc_bf16_f32(128, 128, false, true);   // R K-major  x Gs MN-major
       constexpr uint32_t idesc_b = ptx::idesc_bf16_f32(128, 128, true, true);    // R^T MN-major x Gs MN-major
       const bool do_a = !(p.probe_skip_flush & 4), do_b = !(p.probe_skip_flush & 2);
+      const uint32_t r_base = ptx::smem_u32(r_st), gj_base = ptx::smem_u32(gj_st);
+      const uint32_t gi0 = ptx::smem_u32(gi_st), gi1 = gi0 + kFuTileBytes;
       ptx::mbar_wait(gi_full, 0);
       int it = 0;
       for (int c = 0; c < n_tiles; ++c) {
@@ -148,9 +161,8 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
         const int slot0 = i0 % kFuGjSlots, slot1 = i1 % kFuGjSlots;
         const int s0 = it % kFuRStages, s1 = (it + 1) % kFuRStages;
         const uint32_t ph0 = (it / kFuRStages) & 1, ph1 = ((it + 1) / kFuRStages) & 1;
-        const uint32_t rt0 = ptx::smem_u32(r_st + s0 * kFuTileBytes), rt1 = ptx::smem_u32(r_st + s1 * kFuTileBytes);
-        const uint32_t g0 = ptx::smem_u32(gj_st + slot0 * kFuHalfBytes), g1 = ptx::smem_u32(gj_st + slot1 * kFuHalfBytes);
-        const uint32_t gi0 = ptx::smem_u32(gi_st), gi1 = gi0 + kFuTileBytes;
+        const uint32_t rt0 = r_base + s0 * kFuTileBytes, rt1 = r_base + s1 * kFuTileBytes;
+        const uint32_t g0 = gj_base + slot0 * kFuHalfBytes, g1 = gj_base + slot1 * kFuHalfBytes;
         const uint32_t bacc = tmem_base + 256 + gs * 128;
         it += 2;
         // ---- row block 0: A-product over both Gs_j halves, then the transposed product; the relation stage is
@@ -158,50 +170,63 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
         ptx::mbar_wait(&gj_full[slot0], (i0 / kFuGjSlots) & 1);
         ptx::mbar_wait(&r_full[s0], ph0);
         ptx::tc_fence_after();
-        if (do_a)
+        if (ptx::elect_one()) {
+          if (do_a)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(rt0 + ks * 32, 16, 1024),
-                           ptx::smem_desc_sw128(g0 + ks * 2048, 8192, 1024), idesc_a, (c | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(rt0 + ks * 32, 16, 1024),
+                             ptx::smem_desc_sw128(g0 + ks * 2048, 8192, 1024), idesc_a, (c | ks) != 0);
+        }
+        __syncwarp();
         ptx::mbar_wait(&gj_full[slot1], (i1 / kFuGjSlots) & 1);
         ptx::tc_fence_after();
-        if (do_a)
+        if (ptx::elect_one()) {
+          if (do_a)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(rt0 + 16384 + ks * 32, 16, 1024),
-                           ptx::smem_desc_sw128(g1 + ks * 2048, 8192, 1024), idesc_a, 1);
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(rt0 + 16384 + ks * 32, 16, 1024),
+                             ptx::smem_desc_sw128(g1 + ks * 2048, 8192, 1024), idesc_a, 1);
+        }
+        __syncwarp();
         ptx::mbar_wait(&bacc_empty[gs], ((c >> 1) & 1) ^ 1);       // epilogue has drained this B_acc buffer
         ptx::tc_fence_after();
-        if (do_b)
+        if (ptx::elect_one()) {
+          if (do_b)
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            ptx::umma_bf16(bacc, ptx::smem_desc_sw128(rt0 + ks * 2048, 16384, 1024),
-                           ptx::smem_desc_sw128(gi0 + ks * 2048, 16384, 1024), idesc_b, ks != 0);
-        ptx::umma_commit(&r_empty[s0]);
+            for (int ks = 0; ks < 8; ++ks)
+              ptx::umma_bf16(bacc, ptx::smem_desc_sw128(rt0 + ks * 2048, 16384, 1024),
+                             ptx::smem_desc_sw128(gi0 + ks * 2048, 16384, 1024), idesc_b, ks != 0);
+          ptx::umma_commit(&r_empty[s0]);
+        }
+        __syncwarp();
         // ---- row block 1; each Gs_j half goes back to the ring right after its last use
         ptx::mbar_wait(&r_full[s1], ph1);
         ptx::tc_fence_after();
-        if (do_a)
+        if (ptx::elect_one()) {
+          if (do_a)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            ptx::umma_bf16(tmem_base + 128, ptx::smem_desc_sw128(rt1 + ks * 32, 16, 1024),
-                           ptx::smem_desc_sw128(g0 + ks * 2048, 8192, 1024), idesc_a, (c | ks) != 0);
-        ptx::umma_commit(&gj_empty[slot0]);
-        if (do_a)
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::umma_bf16(tmem_base + 128, ptx::smem_desc_sw128(rt1 + ks * 32, 16, 1024),
+                             ptx::smem_desc_sw128(g0 + ks * 2048, 8192, 1024), idesc_a, (c | ks) != 0);
+          ptx::umma_commit(&gj_empty[slot0]);
+          if (do_a)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            ptx::umma_bf16(tmem_base + 128, ptx::smem_desc_sw128(rt1 + 16384 + ks * 32, 16, 1024),
-                           ptx::smem_desc_sw128(g1 + ks * 2048, 8192, 1024), idesc_a, 1);
-        ptx::umma_commit(&gj_empty[slot1]);
-        if (do_b)
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::umma_bf16(tmem_base + 128, ptx::smem_desc_sw128(rt1 + 16384 + ks * 32, 16, 1024),
+                             ptx::smem_desc_sw128(g1 + ks * 2048, 8192, 1024), idesc_a, 1);
+          ptx::umma_commit(&gj_empty[slot1]);
+          if (do_b)
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            ptx::umma_bf16(bacc, ptx::smem_desc_sw128(rt1 + ks * 2048, 16384, 1024),
-                           ptx::smem_desc_sw128(gi1 + ks * 2048, 16384, 1024), idesc_b, 1);
-        ptx::umma_commit(&r_empty[s1]);
-        ptx::umma_commit(&bacc_full[gs]);
+            for (int ks = 0; ks < 8; ++ks)
+              ptx::umma_bf16(bacc, ptx::smem_desc_sw128(rt1 + ks * 2048, 16384, 1024),
+                             ptx::smem_desc_sw128(gi1 + ks * 2048, 16384, 1024), idesc_b, 1);
+          ptx::umma_commit(&r_empty[s1]);
+          ptx::umma_commit(&bacc_full[gs]);
+        }
+        __syncwarp();
       }
-      ptx::umma_commit(aacc_full);
+      if (ptx::elect_one()) ptx::umma_commit(aacc_full);
+      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- epilogue (warps 2..5)
@@ -236,7 +261,7 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
           }
           ptx::fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (ptx::elect_one()) {                                 // deterministic: always the same lane
             ptx::tma_reduce_add_2d(&tmB, my_stage, q0, brow0);    // rows / columns beyond the tensor are clipped
             ptx::tma_commit_group();
             ptx::tma_wait_read_all();                             // staging reusable
@@ -279,7 +304,9 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
         }
       }
     }
-    if (p.tma_flush && lane == 0) ptx::tma_wait_all();            // reductions performed before the CTA retires
+    __syncwarp();
+    if (p.tma_flush && ptx::elect_one()) ptx::tma_wait_all();     // reductions performed before the CTA retires
+    __syncwarp();
     ptx::tc_fence_before();
   }
   __syncthreads();
