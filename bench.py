@@ -84,7 +84,7 @@ def cpu_arm(n_workload, n_sample, steps, warmup):
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, index):
         threading.Thread.__init__(self, daemon=True)
@@ -108,8 +108,18 @@ class ClockSampler(threading.Thread):
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
+        def num(col):
+            vals = []
+            for r in self.rows:
+                try:
+                    vals.append(float(r[col]))
+                except (IndexError, ValueError):
+                    pass
+            return vals
+        power, limit = num(6), num(7)
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": round(max(power), 1) if power else None,
+                "power_limit_w": round(max(limit), 1) if limit else None}
 
 
 def fused_kernel_active(args):
@@ -209,12 +219,13 @@ def gpu_arm(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     alg_bytes_per_launch = prof_alg / max(1, n_prof)
     traffic, traffic_note = None, None
+    kernel_name = "umma_fused_t_kernel" if os.environ.get("FZ_FUSED_VER", "3") == "4" else "umma_fused_kernel"
     try:   # dram__bytes_read+write per launch from the committed ncu --set full capture, scaled to this launch size
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01b_ncu_traffic.json")))[kernel_name]
         if fused_kernel_active(args):
             traffic = cap["traffic_over_algorithmic"] * alg_bytes_per_launch
             traffic_note = "ncu capture at n=40960: %.4f x algorithmic bytes (%s), scaled to this launch" % (
-                cap["traffic_over_algorithmic"], "profiles/r01_ncu_traffic.json")
+                cap["traffic_over_algorithmic"], cap["raw"])
     except Exception:
         pass
     avg_ms = prof_ms / max(1, n_prof)
@@ -227,6 +238,18 @@ def gpu_arm(args):
                 "avg_launch_ms": round(avg_ms, 4), "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "streamed_bytes_per_launch": prof_bytes / max(1, n_prof),
                 "kernel_share_of_step": round(prof_ms / max(1e-9, e0.elapsed_time(e1)), 4)}
+    if fused:
+        # What actually limits the kernel: with the 2-term split it EXECUTES 2 x 2 x 128 flop per
+        # relation element = 256 flop/B, above the measured ridge (sustained bf16 / HBM), and under random operands the
+        # board sits at its power cap.  Reported next to the algorithmic (HBM) roofline, never instead of it.
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 0.0)) or None
+        executed = 2.0 * 128.0 * args.split_terms * (alg_bytes_per_launch / 2.0)      # flop per launch
+        tf = executed / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        roofline["kernel"] = kernel_name + " (tcgen05/TMA, A and B from one stream of R)"
+        roofline["tensor_executed"] = {"achieved": round(tf, 1), "peak": tf_peak, "unit": "TFLOP/s",
+                                       "frac": round(tf / tf_peak, 4) if tf_peak else None,
+                                       "note": "executed tensor work incl. the 2-term bf16 split (256 flop per relation byte); "
+                                               "peak = MEASURED_PEAKS.json bf16_tflops_sustained"}
 
     # ---- e2e: the same fit through the C ABI with HOST buffers (pinned), H2D of the relations and D2H of the
     # factors / backbones inside the timed region.

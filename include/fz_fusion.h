@@ -112,6 +112,21 @@ int fz_objective(fz_engine* e, double* per_relation, double* total, void* stream
 /* completed relation G_i S_ij G_j^T (base.py:119-146) into a caller buffer */
 int fz_complete(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int mem, void* stream);
 
+/* ---- factor initialisation on the device ------------------------------------------------------
+ * Reference: initialize() / _random_c / _random_vcol, skfusion/fusion/decomposition/_init.py:6-61.  The host keeps the
+ * RandomState (the draws must be consumed bit-exactly) and sends, per object type and per relation touching it, the k_t
+ * lists of p_c = int(0.2 * cols) sampled column indices of the relation oriented with the type on its rows; the engine
+ * computes the column means (a product with a 0/1 selection matrix through the streamed kernels) and accumulates
+ *     G_t = value + sum_relations | mean of the sampled columns |                      (_init.py:36-39, 57-60).
+ * Call order: fz_finalize, then per type fz_init_fill + fz_init_add_sampled_means per relation, then fz_init_end (which
+ * marks every factor as set).  p_c == 0 (fewer than 5 columns) yields NaN factors, as upstream.  Unsharded handles only.
+ * fz_relation_norms returns the 2-norms of the columns (axis 0) or rows (axis 1) of a relation in a HOST buffer: random_c
+ * samples from the int(0.5 * cols) columns of largest norm (_init.py:30-34). */
+int fz_init_fill(fz_engine* e, int t, double value, void* stream);
+int fz_relation_norms(fz_engine* e, int rel, int axis, double* dst_host, void* stream);
+int fz_init_add_sampled_means(fz_engine* e, int t, int rel, const int32_t* idx_host, int p_c, void* stream);
+int fz_init_end(fz_engine* e);
+
 /* ---- measurement ----------------------------------------------------------------------------- */
 /* fz_profile(e, 1) brackets every streamed tensor-core product with CUDA events on its launch stream;
  * fz_profile_read returns how many launches were timed, the sum of their durations, the relation bytes
@@ -126,6 +141,14 @@ int fz_profile_read(fz_engine* e, int64_t* launches, double* total_ms, double* s
  * value(r, c) = splitmix64(seed, (row0 + r) * cols + c) >> 40 / 2^24, rounded to `dtype`.  The same
  * numbers come out of oracle/fusion_oracle.py:hashed_uniform, on any row sharding. */
 int fz_fill_uniform(void* dst, int dtype, int64_t ld, int64_t rows, int64_t cols, int64_t row0, uint64_t seed, void* stream);
+
+/* ---- relation preprocessing on the device -----------------------------------
+ * Replace the unknown (non-finite) entries of a DEVICE-resident rows x cols matrix in place, as Relation.filled() does on
+ * the host (fill_mean / fill_row / fill_col / fill_const, skfusion/fusion/base/fusion_graph.py:464-510):
+ *   mode 0  <- mean of the matrix          1  <- mean of the entry's row        2  <- mean of its column       3  <- value
+ * Means follow numpy.nanmean (NaN skipped, +-inf included), summed in fp64; a row / column without any known entry takes
+ * the matrix mean.  Masked arrays stay a host (numpy) feature. */
+int fz_fill_unknown(void* data, int dtype, int64_t ld, int64_t rows, int64_t cols, int mode, double value, void* stream);
 
 #ifdef __cplusplus
 }

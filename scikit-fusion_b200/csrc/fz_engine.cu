@@ -145,6 +145,10 @@ class EngineBase {
   virtual void get_backbone(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) = 0;
   virtual void objective(double* per_rel, double* total, cudaStream_t st) = 0;
   virtual void complete(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) = 0;
+  virtual void init_fill(int t, double value, cudaStream_t st) = 0;
+  virtual void relation_norms(int rel, int axis, double* dst_host, cudaStream_t st) = 0;
+  virtual void init_add_sampled_means(int t, int rel, const int32_t* idx_host, int p_c, cudaStream_t st) = 0;
+  virtual void init_end() = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -833,6 +837,98 @@ class Engine : public EngineBase {
     CUDA_OK(cudaStreamSynchronize(st));
   }
 
+  // ---------------------------------------------------------------------------------------------
+  // Factor initialisation on the device (reference _init.py:20-61).  The host draws the
+  // column samples with numpy's RandomState (bit-exact RNG consumption); the O(k n^2) part -- the means over the sampled
+  // columns -- is the product  view(R) * W  with a 0/1 selection matrix W, run through the same streamed kernels as the
+  // iteration.  G_t = value + sum over relations touching t of | view * W / p_c |.
+  void init_fill(int t, double value, cudaStream_t st) override {
+    need_final();
+    if (t < 0 || t >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id %d", t);
+    TypeRec& Tt = *types_[t];
+    fill_value<T><<<nblk(Tt.n * Tt.k, 256), 256, 0, st>>>(cur(Tt), (T)value, Tt.n * Tt.k);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+  }
+  // 2-norms of the columns (axis 0) or rows (axis 1) of a relation, fp64, into a HOST buffer (random_c ranks the
+  // columns of the oriented relation by norm, _init.py:32-34)
+  void relation_norms(int rel, int axis, double* dst_host, cudaStream_t st) override {
+    need_final();
+    if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "device initialisation on sharded handles is not implemented");
+    RelRec& r = relation(rel);
+    if (r.theta) FZ_THROW(FZ_ERR_INVALID, "constraint matrices do not seed factors");
+    const int64_t count = axis == 0 ? r.cols : r.rows_loc;
+    DevBuf out;
+    out.alloc((size_t)std::max<int64_t>(1, count) * 8);
+    if (axis == 0) {
+      const int chunks = (int)std::min<int64_t>(64, std::max<int64_t>(1, (r.rows_loc + 255) / 256));
+      const int64_t rows_per_chunk = (r.rows_loc + chunks - 1) / chunks;
+      DevBuf part;
+      part.alloc((size_t)chunks * r.cols * 8);
+      dim3 g(nblk(r.cols, 256), chunks);
+      if (r.storage == FZ_BF16) col_sumsq_partial<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, rows_per_chunk, part.template as<double>());
+      else col_sumsq_partial<T><<<g, 256, 0, st>>>((const T*)r.data, r.ld, r.rows_loc, r.cols, rows_per_chunk, part.template as<double>());
+      sqrt_of_chunk_sums<<<nblk(r.cols, 256), 256, 0, st>>>(part.template as<double>(), out.template as<double>(), chunks, r.cols);
+      launches += 2;
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaMemcpyAsync(dst_host, out.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+    } else {
+      if (r.storage == FZ_BF16) row_norms<__nv_bfloat16><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, out.template as<double>());
+      else row_norms<T><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const T*)r.data, r.ld, r.rows_loc, r.cols, out.template as<double>());
+      ++launches;
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaMemcpyAsync(dst_host, out.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+    }
+  }
+  // idx_host: [k_t][p_c] column indices of the oriented relation (t on the rows), one row per latent column
+  void init_add_sampled_means(int t, int rel, const int32_t* idx_host, int p_c, cudaStream_t st) override {
+    need_final();
+    if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "device initialisation on sharded handles is not implemented");
+    if (t < 0 || t >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id %d", t);
+    RelRec& r = relation(rel);
+    if (r.theta || (r.ti != t && r.tj != t)) FZ_THROW(FZ_ERR_INVALID, "relation %d does not touch type %d", rel, t);
+    if (p_c < 0) FZ_THROW(FZ_ERR_INVALID, "negative sample size");
+    TypeRec& Tt = *types_[t];
+    const bool row_role = (r.ti == t);
+    TypeRec& To = row_role ? *types_[r.tj] : *types_[r.ti];     // the type the sampled columns index
+    // W (n_other x k_t), ones at the sampled positions
+    r.E.alloc((size_t)To.n * Tt.k * sizeof(T));
+    if (p_c > 0) {
+      DevBuf idx;
+      idx.alloc((size_t)Tt.k * p_c * sizeof(int32_t), false);
+      CUDA_OK(cudaMemcpyAsync(idx.p, idx_host, (size_t)Tt.k * p_c * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      scatter_ones<T><<<nblk((long long)Tt.k * p_c, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, (const int32_t*)idx.p, Tt.k, p_c, To.n);
+      ++launches;
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaStreamSynchronize(st));                       // idx is freed at scope exit
+    }
+    r.Cx.alloc((size_t)Tt.n * Tt.k * sizeof(T));
+    if (r.storage == FZ_BF16) {
+      r.Es.alloc((size_t)To.n * terms_ * kKp * 2);
+      split_factor<T><<<nblk(To.n * kKp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(), To.n, To.n,
+                                                              Tt.k, kKp, terms_);
+      ++launches;
+      std::string e;
+      if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 64, &e))
+        FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+      umma(r, /*trans=*/!row_role, r.tmEs, 0, r.Cx.template as<T>(), Tt.k, (int)Tt.n, (int)To.n, Tt.k, st);
+    } else {
+      if (row_role) gemm((const T*)r.data, r.ld, r.E.template as<T>(), Tt.k, r.Cx.template as<T>(), Tt.k, (int)Tt.n, Tt.k, (int)To.n, false, st);
+      else gemm_t((const T*)r.data, r.ld, r.E.template as<T>(), Tt.k, r.Cx.template as<T>(), Tt.k, (int)Tt.n, Tt.k, (int)To.n, st);
+    }
+    add_abs_mean<T><<<nblk(Tt.n * Tt.k, 256), 256, 0, st>>>(r.Cx.template as<T>(), cur(Tt), Tt.n * Tt.k, (T)p_c);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+  }
+  void init_end() override {
+    need_final();
+    CUDA_OK(cudaDeviceSynchronize());
+    for (auto& rp : rels_) { rp->E.release(); rp->Es.release(); rp->Cx.release(); }
+    for (auto& tp : types_) tp->has_factor = true;
+  }
+
  private:
   // ---------------------------------------------------------------------------------------------
   void need_final() const {
@@ -1249,6 +1345,50 @@ struct fz_engine {
   }                                                              \
   return FZ_OK;
 
+// ---- unknown-value replacement on a device-resident matrix (fusion_graph.py:464-510), in place
+namespace {
+template <class XT>
+int fill_unknown_impl(XT* X, int64_t ld, int64_t rows, int64_t cols, int mode, double value, cudaStream_t st) {
+  using namespace fz;
+  if (mode == 3) {
+    replace_unknown<XT><<<nblk(rows * cols, 256), 256, 0, st>>>(X, ld, rows, cols, 3, nullptr, nullptr, value);
+    return cudaGetLastError() == cudaSuccess ? FZ_OK : FZ_ERR_CUDA;
+  }
+  const bool by_col = (mode == 2);
+  const int64_t n_axis = by_col ? cols : rows;
+  double *sum = nullptr, *cnt = nullptr, *total = nullptr, *psum = nullptr, *pcnt = nullptr;
+  if (cudaMalloc(&sum, (size_t)n_axis * 8) != cudaSuccess || cudaMalloc(&cnt, (size_t)n_axis * 8) != cudaSuccess ||
+      cudaMalloc(&total, 16) != cudaSuccess) {
+    cudaFree(sum); cudaFree(cnt); cudaFree(total);
+    return FZ_ERR_NOMEM;
+  }
+  int rc = FZ_OK;
+  if (!by_col) {
+    row_nan_stats<XT><<<nblk(rows, 8), 256, 0, st>>>(X, ld, rows, cols, sum, cnt);
+  } else {
+    const int chunks = (int)std::min<int64_t>(64, std::max<int64_t>(1, (rows + 255) / 256));
+    const int64_t rpc = (rows + chunks - 1) / chunks;
+    if (cudaMalloc(&psum, (size_t)chunks * cols * 8) != cudaSuccess || cudaMalloc(&pcnt, (size_t)chunks * cols * 8) != cudaSuccess) {
+      rc = FZ_ERR_NOMEM;
+    } else {
+      dim3 g(nblk(cols, 256), chunks);
+      col_nan_stats_partial<XT><<<g, 256, 0, st>>>(X, ld, rows, cols, rpc, psum, pcnt);
+      sum_chunks<<<nblk(cols, 256), 256, 0, st>>>(psum, sum, chunks, cols);
+      sum_chunks<<<nblk(cols, 256), 256, 0, st>>>(pcnt, cnt, chunks, cols);
+    }
+  }
+  if (rc == FZ_OK) {
+    finish_means<<<1, 1024, 0, st>>>(sum, cnt, n_axis, total);
+    replace_unknown<XT><<<nblk(rows * cols, 256), 256, 0, st>>>(X, ld, rows, cols, mode, total, sum, 0.0);
+    if (cudaGetLastError() != cudaSuccess) rc = FZ_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = FZ_ERR_CUDA;   // temporaries are freed below
+  }
+  cudaFree(sum); cudaFree(cnt); cudaFree(total); cudaFree(psum); cudaFree(pcnt);
+  return rc;
+}
+}  // namespace
+
+
 extern "C" {
 
 int fz_version(void) { return 100; }
@@ -1361,6 +1501,19 @@ int fz_complete(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int
   FZ_GUARD(e, e->impl->complete(rel, dst, ld, dst_dtype, mem, (cudaStream_t)stream))
 }
 
+int fz_init_fill(fz_engine* e, int t, double value, void* stream) {
+  FZ_GUARD(e, e->impl->init_fill(t, value, (cudaStream_t)stream))
+}
+int fz_relation_norms(fz_engine* e, int rel, int axis, double* dst_host, void* stream) {
+  FZ_GUARD(e, e->impl->relation_norms(rel, axis, dst_host, (cudaStream_t)stream))
+}
+int fz_init_add_sampled_means(fz_engine* e, int t, int rel, const int32_t* idx_host, int p_c, void* stream) {
+  FZ_GUARD(e, e->impl->init_add_sampled_means(t, rel, idx_host, p_c, (cudaStream_t)stream))
+}
+int fz_init_end(fz_engine* e) {
+  FZ_GUARD(e, e->impl->init_end())
+}
+
 int fz_profile(fz_engine* e, int enable) {
   if (!e || !e->impl) return FZ_ERR_INVALID;
   e->impl->profile = enable != 0;
@@ -1396,6 +1549,16 @@ int fz_fill_uniform(void* dst, int dtype, int64_t ld, int64_t rows, int64_t cols
   else if (dtype == FZ_F64) fz::fill_hashed_uniform<double><<<g, 256, 0, st>>>((double*)dst, ld, rows, cols, row0, seed);
   else return FZ_ERR_INVALID;
   return cudaGetLastError() == cudaSuccess ? FZ_OK : FZ_ERR_CUDA;
+}
+
+int fz_fill_unknown(void* data, int dtype, int64_t ld, int64_t rows, int64_t cols, int mode, double value, void* stream) {
+  if (!data || rows < 0 || cols < 0 || ld < cols || mode < 0 || mode > 3) return FZ_ERR_INVALID;
+  if (rows * cols == 0) return FZ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FZ_BF16) return fill_unknown_impl<__nv_bfloat16>((__nv_bfloat16*)data, ld, rows, cols, mode, value, st);
+  if (dtype == FZ_F32) return fill_unknown_impl<float>((float*)data, ld, rows, cols, mode, value, st);
+  if (dtype == FZ_F64) return fill_unknown_impl<double>((double*)data, ld, rows, cols, mode, value, st);
+  return FZ_ERR_INVALID;
 }
 
 }  // extern "C"

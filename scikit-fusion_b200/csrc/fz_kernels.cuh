@@ -381,6 +381,152 @@ fused_update(const UpdArgs<T> a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// replacing unknown (non-finite) entries of a device-resident relation before the fit
+// (reference fill_mean / fill_row / fill_col / fill_const, skfusion/fusion/base/fusion_graph.py:464-510).
+// numpy.nanmean semantics: NaN entries are skipped, +-inf take part in the mean.
+// ------------------------------------------------------------------------------------------------
+template <class XT> __device__ __forceinline__ XT store_as(double v) { return static_cast<XT>(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 store_as<__nv_bfloat16>(double v) { return __float2bfloat16_rn((float)v); }
+
+// per row: sum and count of the non-NaN entries (one warp per row, fixed-order shuffle reduction)
+template <class XT>
+__global__ void row_nan_stats(const XT* __restrict__ X, long long ld, long long rows, long long cols, double* __restrict__ sum,
+                              double* __restrict__ cnt) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  double s = 0.0, c = 0.0;
+  for (long long j = lane; j < cols; j += 32) {
+    const double v = load_as<XT, double>(X + r * ld + j);
+    if (v == v) { s += v; c += 1.0; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) { sum[r] = s; cnt[r] = c; }
+}
+// per column and row chunk: part_sum[chunk][col], part_cnt[chunk][col]
+template <class XT>
+__global__ void col_nan_stats_partial(const XT* __restrict__ X, long long ld, long long rows, long long cols, long long rows_per_chunk,
+                                      double* __restrict__ part_sum, double* __restrict__ part_cnt) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  double s = 0.0, n = 0.0;
+  for (long long r = r0; r < r1; ++r) {
+    const double v = load_as<XT, double>(X + r * ld + c);
+    if (v == v) { s += v; n += 1.0; }
+  }
+  part_sum[(long long)blockIdx.y * cols + c] = s;
+  part_cnt[(long long)blockIdx.y * cols + c] = n;
+}
+__global__ void sum_chunks(const double* __restrict__ part, double* __restrict__ out, int chunks, long long cols) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double s = 0.0;
+  for (int k = 0; k < chunks; ++k) s += part[(long long)k * cols + c];
+  out[c] = s;
+}
+// one block: total[0] = sum(sum[i]), total[1] = sum(cnt[i]) in a fixed order; then mean[i] = sum[i]/cnt[i], or the overall
+// mean where a row / column has no known entry (NaN mean)
+__global__ void finish_means(double* __restrict__ sum, const double* __restrict__ cnt, long long n, double* __restrict__ total) {
+  __shared__ double ss[1024], sc[1024];
+  double s = 0.0, c = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) { s += sum[i]; c += cnt[i]; }
+  ss[threadIdx.x] = s; sc[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { ss[threadIdx.x] += ss[threadIdx.x + o]; sc[threadIdx.x] += sc[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const double overall = ss[0] / sc[0];
+  if (threadIdx.x == 0) { total[0] = overall; }
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double m = sum[i] / cnt[i];
+    sum[i] = (m == m) ? m : overall;
+  }
+}
+// mode 0: every unknown <- scalar[0];  1: <- per_axis[row];  2: <- per_axis[col];  3: <- value
+template <class XT>
+__global__ void replace_unknown(XT* __restrict__ X, long long ld, long long rows, long long cols, int mode, const double* __restrict__ scalar,
+                                const double* __restrict__ per_axis, double value) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols, c = idx % cols;
+  const double v = load_as<XT, double>(X + r * ld + c);
+  if (v == v && v - v == 0.0) return;            // finite
+  double w = value;
+  if (mode == 0) w = scalar[0];
+  else if (mode == 1) w = per_axis[r];
+  else if (mode == 2) w = per_axis[c];
+  X[r * ld + c] = store_as<XT>(w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// factor initialisation on the device (reference _init.py:20-61)
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void fill_value(T* __restrict__ dst, T value, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = value;
+}
+// W[idx[c][s]][c] = 1   (W is n_other x k, leading dimension ldw)
+template <class T>
+__global__ void scatter_ones(T* __restrict__ W, long long ldw, const int32_t* __restrict__ idx, int k, int p_c, long long n_other) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)k * p_c) return;
+  const int c = (int)(i / p_c);
+  const long long row = idx[i];
+  if (row >= 0 && row < n_other) W[row * ldw + c] = T(1);
+}
+// G += | P / count |      (numpy: mean = sum / count; count == 0 gives NaN like the mean of an empty slice)
+template <class T>
+__global__ void add_abs_mean(const T* __restrict__ P, T* __restrict__ G, long long n, T count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T m = P[i] / count;
+  G[i] += (m < T(0)) ? -m : m;
+}
+// partial sums of squares of the columns over a chunk of rows: part[chunk][col]
+template <class XT>
+__global__ void col_sumsq_partial(const XT* __restrict__ X, long long ld, long long rows, long long cols, long long rows_per_chunk,
+                                  double* __restrict__ part) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  double s = 0.0;
+  for (long long r = r0; r < r1; ++r) {
+    const double v = load_as<XT, double>(X + r * ld + c);
+    s += v * v;
+  }
+  part[(long long)blockIdx.y * cols + c] = s;
+}
+__global__ void sqrt_of_chunk_sums(const double* __restrict__ part, double* __restrict__ out, int chunks, long long cols) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double s = 0.0;
+  for (int k = 0; k < chunks; ++k) s += part[(long long)k * cols + c];
+  out[c] = sqrt(s);
+}
+// one warp per row, lanes stride over the columns, fixed-order shuffle reduction
+template <class XT>
+__global__ void row_norms(const XT* __restrict__ X, long long ld, long long rows, long long cols, double* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (long long c = lane; c < cols; c += 32) {
+    const double v = load_as<XT, double>(X + r * ld + c);
+    s += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = sqrt(s);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Factor -> tensor-core operand form: Gs[r][t*kp + q] = bf16 term t of the running residual of G[r][q].
 // Rows >= n_valid and columns >= k are zero.  (Own design: no counterpart in the reference.)
 // ------------------------------------------------------------------------------------------------

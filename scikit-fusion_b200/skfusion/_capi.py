@@ -25,6 +25,7 @@ SYMBOLS = [
     "fz_phase_products", "fz_phase_update", "fz_phase_products_begin", "fz_phase_product_relation", "fz_phase_products_end", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
     "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete",
     "fz_fill_uniform", "fz_profile", "fz_profile_read",
+    "fz_init_fill", "fz_relation_norms", "fz_init_add_sampled_means", "fz_init_end", "fz_fill_unknown",
 ]
 
 
@@ -100,6 +101,11 @@ def lib():
         "fz_objective": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]),
         "fz_complete": (i32, [vp, i32, vp, i64, i32, i32, vp]),
         "fz_fill_uniform": (i32, [vp, i32, i64, i64, i64, i64, ctypes.c_uint64, vp]),
+        "fz_init_fill": (i32, [vp, i32, ctypes.c_double, vp]),
+        "fz_relation_norms": (i32, [vp, i32, i32, ctypes.POINTER(ctypes.c_double), vp]),
+        "fz_init_add_sampled_means": (i32, [vp, i32, i32, ctypes.POINTER(ctypes.c_int32), i32, vp]),
+        "fz_init_end": (i32, [vp]),
+        "fz_fill_unknown": (i32, [vp, i32, i64, i64, i64, i32, ctypes.c_double, vp]),
         "fz_profile": (i32, [vp, i32]),
         "fz_profile_read": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(ctypes.c_double)]),
@@ -135,6 +141,20 @@ def fill_uniform(tensor, seed, row0=0, stream=0):
                                int(tensor.shape[0]), int(tensor.shape[1]), int(row0), int(seed), ctypes.c_void_p(stream))
     if rc != 0:
         raise EngineError("fz_fill_uniform failed (%d)" % rc)
+    return tensor
+
+
+FILL_MODES = {"mean": 0, "row_mean": 1, "col_mean": 2, "const": 3}
+
+
+def fill_unknown(tensor, mode, value=0.0, stream=0):
+    """Replace the non-finite entries of a 2-D torch CUDA tensor IN PLACE (see fz_fill_unknown); returns the tensor."""
+    if not _is_torch_cuda(tensor) or tensor.dim() != 2 or tensor.stride(1) != 1:
+        raise ValueError("fill_unknown needs a 2-D torch CUDA tensor with unit inner stride")
+    rc = lib().fz_fill_unknown(ctypes.c_void_p(tensor.data_ptr()), dtype_code(str(tensor.dtype)), int(tensor.stride(0)),
+                               int(tensor.shape[0]), int(tensor.shape[1]), FILL_MODES[mode], float(value), ctypes.c_void_p(stream))
+    if rc != 0:
+        raise EngineError("fz_fill_unknown failed (%d)" % rc)
     return tensor
 
 
@@ -330,6 +350,30 @@ class Engine(object):
         out = np.empty((ni, nj), dtype=np.float64)
         self._ck(self._L.fz_complete(self._h, rel, ctypes.c_void_p(out.ctypes.data), nj, FZ_F64, FZ_HOST, ctypes.c_void_p(stream)))
         return out
+
+    # ---- factor initialisation on the device (_init.py:20-61; the RNG stays on the host)
+    def init_fill(self, t, value, stream=0):
+        self._ck(self._L.fz_init_fill(self._h, int(t), float(value), ctypes.c_void_p(stream)))
+
+    def relation_norms(self, rel, axis, stream=0):
+        """2-norms of the columns (axis=0) or rows (axis=1) of relation ``rel`` as float64 numpy."""
+        ti, tj = self.rel_types[rel]
+        count = self.type_shape[tj][0] if axis == 0 else self.type_shape[ti][0]
+        out = np.empty(count, dtype=np.float64)
+        self._ck(self._L.fz_relation_norms(self._h, int(rel), int(axis), out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                           ctypes.c_void_p(stream)))
+        return out
+
+    def init_add_sampled_means(self, t, rel, idx, stream=0):
+        """idx: (k_t, p_c) int32 -- per latent column the sampled columns of the relation oriented with t on its rows."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        if idx.ndim != 2 or idx.shape[0] != self.type_shape[t][1]:
+            raise ValueError("index array has shape %r, expected (%d, p_c)" % (idx.shape, self.type_shape[t][1]))
+        self._ck(self._L.fz_init_add_sampled_means(self._h, int(t), int(rel), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                                   int(idx.shape[1]), ctypes.c_void_p(stream)))
+
+    def init_end(self):
+        self._ck(self._L.fz_init_end(self._h))
 
     def profile(self, enable=True):
         self._ck(self._L.fz_profile(self._h, 1 if enable else 0))

@@ -16,11 +16,12 @@ from itertools import product
 import numpy as np
 
 from . import solver
+from .. import _capi
 from .graph import DataFusionError
 
 __all__ = ['FusionBase', 'FusionFit', 'FusionTransform', 'DataFusionError', 'Dfmf', 'Dfmc', 'DfmfTransform']
 
-_ENGINE_KEYS = ("device", "dtype", "storage", "split_terms")
+_ENGINE_KEYS = ("device", "dtype", "storage", "split_terms", "device_init")
 
 
 class FusionBase(object):
@@ -238,10 +239,13 @@ class DfmfTransform(FusionTransform):
         for row_type, col_type in product(fusion_graph.object_types, repeat=2):
             for relation in fusion_graph.get_relations(row_type, col_type):
                 data = relation.preprocessor(relation.data) if relation.preprocessor else relation.data
-                if np.ma.is_masked(data):
-                    data.fill_value = self.fill_value
-                    data = data.filled()
-                data[~np.isfinite(data)] = self.fill_value       # in place, as upstream (dfmf.py:185)
+                if _capi._is_torch_cuda(data):
+                    _capi.fill_unknown(data, "const", self.fill_value)      # in place, on the device
+                else:
+                    if np.ma.is_masked(data):
+                        data.fill_value = self.fill_value
+                        data = data.filled()
+                    data[~np.isfinite(data)] = self.fill_value       # in place, as upstream (dfmf.py:185)
                 block = R if relation.row_type != relation.col_type else T
                 block.setdefault((relation.row_type, relation.col_type), []).append(data)
 

@@ -89,6 +89,10 @@ def fill_const(x, const):
     return out
 
 
+def _is_device_tensor(x):
+    return hasattr(x, "data_ptr") and bool(getattr(x, "is_cuda", False))
+
+
 FILL_CONST = 'const'
 FILL_TYPE = {'mean': fill_mean, 'row_mean': fill_row, 'col_mean': fill_col, 'const': fill_const}
 
@@ -119,7 +123,13 @@ class Relation(object):
         self._id = name or uuid1()
 
     def filled(self):
-        """A copy of the data with unknown values replaced according to ``fill_value``."""
+        """A copy of the data with unknown values replaced according to ``fill_value``.  Device-resident data (a torch
+        CUDA tensor) is copied and filled on the GPU (fz_fill_unknown); it never visits the host."""
+        if _is_device_tensor(self.data):
+            from .. import _capi
+            if isinstance(self.fill_value, Number):
+                return _capi.fill_unknown(self.data.clone(), FILL_CONST, self.fill_value)
+            return _capi.fill_unknown(self.data.clone(), self.fill_value)
         if isinstance(self.fill_value, Number):
             return FILL_TYPE[FILL_CONST](self.data, self.fill_value)
         return FILL_TYPE[self.fill_value](self.data)

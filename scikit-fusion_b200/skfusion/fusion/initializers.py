@@ -57,3 +57,50 @@ def initialize(obj_types, obj_type2n_obj, obj_type2rank, R, init_type, random_st
             total = total + np.abs(_sampled_means(view, pool, shape[1], random_state))
         factors[obj_type, obj_type] = total
     return factors
+
+
+# ------------------------------------------------------------------------------------------------
+# The same initialisation with the O(k n^2) part on the GPU.  The host still owns the RandomState: it draws, in the
+# reference's order, the shuffles that pick the sampled columns (so the RNG stream is consumed bit-exactly), and the
+# engine computes the column means as a product with a 0/1 selection matrix (include/fz_fusion.h, fz_init_*).
+# Differences from the host path are floating-point only: the means are summed in the engine's compute dtype in the
+# kernels' order instead of numpy's pairwise order, and random_c ranks columns by norms computed on the device
+# (ties between columns whose norms differ in the last bits could order differently).
+# ------------------------------------------------------------------------------------------------
+def sample_plan(n_cols, rank, norms, random_state):
+    """The (rank, p_c) index array the reference's inner loop would use on a relation with ``n_cols`` columns:
+    cumulative in-place shuffles of the pool, first p_c entries each time (_init.py:35-38, 55-59).  ``norms`` is None
+    for random_vcol, the column 2-norms for random_c."""
+    sample = int(.2 * n_cols)
+    if norms is None:
+        pool = np.arange(n_cols)
+    else:
+        keep = int(.5 * n_cols)
+        heavy = sorted(enumerate(norms), key=lambda pair: pair[1], reverse=True)[:keep]
+        pool = np.array([col for col, _ in heavy], dtype=np.int64)   # shuffling an array or a list draws the same numbers
+    plan = np.empty((rank, sample), dtype=np.int32)
+    for col in range(rank):
+        random_state.shuffle(pool)
+        plan[col] = pool[:sample]
+    return plan
+
+
+def initialize_on_device(engine, type_id, rel_of_pair, obj_types, obj_type2rank, pairs, n_of, init_type, random_state):
+    """Device-side twin of ``initialize`` for init_type random_c / random_vcol.
+    rel_of_pair[(ti, tj)] = engine id of the FIRST relation of that pair (_dfmf.py:191); ``pairs`` lists the pairs in
+    the R dict's order; n_of[t] = objects of type t."""
+    if init_type not in ("random_c", "random_vcol"):
+        raise KeyError(init_type)
+    for obj_type in obj_types:
+        tid = type_id[obj_type]
+        engine.init_fill(tid, 1e-5)
+        for pair in pairs:
+            if obj_type not in pair:
+                continue
+            rel = rel_of_pair[pair]
+            row_role = obj_type == pair[0]
+            other = pair[1] if row_role else pair[0]
+            norms = engine.relation_norms(rel, 0 if row_role else 1) if init_type == "random_c" else None
+            plan = sample_plan(n_of[other], int(obj_type2rank[obj_type]), norms, random_state)
+            engine.init_add_sampled_means(tid, rel, plan)
+    engine.init_end()

@@ -11,6 +11,10 @@ Defaults can be changed process-wide (``engine_options.update(dtype='float64')``
   storage      device dtype of relation matrices: None (= dtype), or 'bfloat16' to take the
                tcgen05 tensor-core path (rank <= 64, fp32 engine)
   split_terms  bf16 terms used to represent a factor on the tensor-core path (1..3)
+  device_init  where the data-driven initialisations (random_c / random_vcol) compute their column means: 'auto'
+               (default: on the GPU when a relation is already device-resident or the graph has more than
+               AUTO_FP64_MAX_ENTRIES entries, otherwise with numpy on the host exactly like the reference), True, False.
+               The RandomState is consumed identically either way (initializers.py).
 """
 import os
 
@@ -19,6 +23,7 @@ engine_options = {
     "dtype": os.environ.get("SKFUSION_B200_DTYPE", "auto"),
     "storage": os.environ.get("SKFUSION_B200_STORAGE") or None,
     "split_terms": int(os.environ.get("SKFUSION_B200_SPLIT_TERMS", "2")),
+    "device_init": {"1": True, "0": False}.get(os.environ.get("SKFUSION_B200_DEVICE_INIT", ""), "auto"),
 }
 
 

@@ -15,7 +15,7 @@ import logging
 import numpy as np
 
 from .. import _capi
-from .initializers import initialize
+from .initializers import initialize, initialize_on_device
 from .options import resolve
 
 log = logging.getLogger("skfusion.fusion")
@@ -107,8 +107,11 @@ def _fit(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopp
     _configure_logging(verbose)
     opts = resolve(n_entries=_count_entries(R, Theta), **engine_kwargs)
     sizes = count_objects(obj_types, R)
-    first = {key: _host_view(mats[0]) for key, mats in R.items()} if init_type != "random" else {}
-    G0 = initialize(obj_types, sizes, obj_type2rank, first, init_type, random_state)
+    on_device = _init_on_device(opts, init_type, R, Theta)
+    G0 = None
+    if not on_device:
+        first = {key: _host_view(mats[0]) for key, mats in R.items()} if init_type != "random" else {}
+        G0 = initialize(obj_types, sizes, obj_type2rank, first, init_type, random_state)
     if stopping_system:
         compute_err = True
 
@@ -116,9 +119,17 @@ def _fit(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopp
     try:
         prob.add_types(obj_types, sizes, obj_type2rank)
         prob.add_blocks(R, Theta, M)
-        for t in obj_types:
-            prob.engine.set_factor(prob.type_id[t], G0[t, t])
-        prob.engine.finalize()
+        if on_device:
+            # random_c / random_vcol with the O(k n^2) column means on the GPU; the RNG is consumed on the host
+            prob.engine.finalize()
+            initialize_on_device(prob.engine, prob.type_id, {key: ids[0] for key, ids in prob.rel_ids.items()}, list(obj_types),
+                                 obj_type2rank, list(R.keys()), sizes, init_type, random_state)
+            if max_iter <= 0 or stopping or compute_err or callback:
+                G0 = prob.factors()
+        else:
+            for t in obj_types:
+                prob.engine.set_factor(prob.type_id[t], G0[t, t])
+            prob.engine.finalize()
 
         interactive = bool(stopping or compute_err or callback)
         if not interactive:
@@ -158,6 +169,18 @@ def _fit(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopp
         return G, S
     finally:
         prob.close()
+
+
+def _init_on_device(opts, init_type, R, Theta):
+    """Where random_c / random_vcol compute their column means (options.py: device_init)."""
+    if init_type == "random":
+        return False
+    choice = opts.get("device_init", "auto")
+    if choice in (True, False):
+        return choice
+    from .options import AUTO_FP64_MAX_ENTRIES
+    resident = any(_capi._is_torch_cuda(mat) for mats in R.values() for mat in mats)
+    return resident or _count_entries(R, Theta) > AUTO_FP64_MAX_ENTRIES
 
 
 def _target_of(stopping):
