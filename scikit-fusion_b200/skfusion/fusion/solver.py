@@ -238,10 +238,13 @@ def transform(R_ij, Theta_i, target_obj_type, obj_type2rank, G, S, max_iter=10, 
     if len(set(n_targets)) > 1:
         log.critical("Target object type: %s size mismatch" % tgt)
     n_new = n_targets[0]
-    first = {key: _host_view(mats[0]) for key, mats in R_ij.items()} if init_type != "random" else {}
-    G_i = initialize([tgt], {tgt: n_new}, obj_type2rank, first, init_type, random_state)[tgt, tgt]
-    if max_iter <= 0:
-        return G_i
+    on_device = _init_on_device(opts, init_type, R_ij, Theta_i)
+    G_i = None
+    if not on_device:
+        first = {key: _host_view(mats[0]) for key, mats in R_ij.items()} if init_type != "random" else {}
+        G_i = initialize([tgt], {tgt: n_new}, obj_type2rank, first, init_type, random_state)[tgt, tgt]
+        if max_iter <= 0:
+            return G_i
 
     prob = _Problem(opts)
     try:
@@ -268,8 +271,19 @@ def transform(R_ij, Theta_i, target_obj_type, obj_type2rank, G, S, max_iter=10, 
             for mat in mats:
                 prob.engine.add_relation(prob.type_id[id(tgt)], prob.type_id[id(tgt)], mat, storage=None)
         for t in involved:
-            prob.engine.set_factor(prob.type_id[id(t)], G_i if t is tgt else G[t, t])
+            if not (on_device and t is tgt):
+                prob.engine.set_factor(prob.type_id[id(t)], G_i if t is tgt else G[t, t])
         prob.engine.finalize()
+        if on_device:
+            # the target's random_c / random_vcol seed with its column means computed on the GPU (RNG on the host)
+            first_rel = {}
+            for rid, key, l in rel_of:
+                first_rel.setdefault(key, rid)
+            n_of = {t: (n_new if t is tgt else G[t, t].shape[0]) for t in involved}
+            initialize_on_device(prob.engine, {tgt: prob.type_id[id(tgt)]}, first_rel, [tgt], obj_type2rank,
+                                 [key for key in R_ij.keys() if key in first_rel], n_of, init_type, random_state)
+            if max_iter <= 0:
+                return prob.engine.get_factor(prob.type_id[id(tgt)])
         for rid, key, l in rel_of:
             prob.engine.set_backbone(rid, S[key][l])
         prob.engine.transform_prepare(prob.type_id[id(tgt)])

@@ -135,3 +135,26 @@ def test_estimator_uses_device_init_for_device_resident_relations():
         fusion.FusionGraph([fusion.Relation(torch.from_numpy(R12.astype(np.float32)).cuda(), t1, t2)]))
     for t in (t1, t2):
         assert rel_fro(host.factor(t), dev.factor(t)) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("init_type", ["random_vcol", "random_c"])
+def test_transform_seeded_on_the_device_follows_the_oracle(init_type):
+    """DfmfTransform's default seed is the fuser's data-driven one (dfmf.py:169): the target's column means on the GPU."""
+    import cases
+    from skfusion.fusion import solver
+    n, n_new, k = 200, 150, 12
+    types, ranks, R = oracle.hashed_graph(n, n_types=3, rank=k, storage="float64")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Go, So = oracle.dfmf(R, {}, types, ranks, max_iter=10, init_type="random", random_state=np.random.RandomState(0))
+        tags = {t: cases.Tag(t) for t in types}
+        G = {(tags[t], tags[t]): Go[t, t] for t in types}
+        S = {(tags[a], tags[b]): So[a, b] for (a, b) in So}
+        R_new = {(tags[0], tags[1]): [oracle.hashed_uniform(77, n_new, n)], (tags[0], tags[2]): [oracle.hashed_uniform(78, n_new, n)]}
+        rk = {tags[t]: k for t in types}
+        for iters in (0, 25):
+            ref = oracle.transform(R_new, {}, tags[0], rk, G, S, max_iter=iters, init_type=init_type, random_state=np.random.RandomState(3))
+            got = solver.transform(R_new, {}, tags[0], rk, G, S, max_iter=iters, init_type=init_type,
+                                   random_state=np.random.RandomState(3), dtype="float64", device_init=True)
+            assert rel_fro(ref, got) < 1e-9, (iters, rel_fro(ref, got))
