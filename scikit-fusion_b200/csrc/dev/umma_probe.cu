@@ -340,7 +340,7 @@ static int run_fused_t_case(int rows, int cols, int ka, int kb, int csplit, int 
   CUtensorMap tr, tgj, tb; std::string err;
   if (kb % 4 != 0) tma_flush = 0;
   bool ok = make_tmap_bf16_2d(&tr, dX, rows, cols, ld, 64, 256, &err) && make_tmap_bf16_2d(&tgj, dGjT, 128, ldtj, ldtj, 64, 128, &err);
-  if (ok && tma_flush) ok = make_tmap_generic(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dB, cols, kb, kb, 16, 64, CU_TENSOR_MAP_SWIZZLE_NONE, &err);
+  if (ok && tma_flush) ok = make_tmap_generic(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dB, cols, kb, kb, tma_flush == 2 ? 64 : 16, 64, CU_TENSOR_MAP_SWIZZLE_NONE, &err);
   if (!tma_flush) tb = tr;
   if (!ok) { printf("fusedT rows=%d cols=%d ka=%d kb=%d: tmap error: %s  FAIL\n", rows, cols, ka, kb, err.c_str()); return 1; }
   FusedTParams p;
@@ -373,12 +373,12 @@ static int run_fused_t_case(int rows, int cols, int ka, int kb, int csplit, int 
     }
   const bool good = ea / ma < 2e-5 && eb / mb < 2e-5;
   printf("fusedT rows=%d cols=%d ka=%d kb=%d csplit=%d flush=%s variant=%d gi_row0=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka,
-         kb, splits, tma_flush ? "tma" : "red", variant, gi_row0, ea / ma, eb / mb, good ? "OK" : "FAIL");
+         kb, splits, tma_flush == 2 ? "tma64" : (tma_flush ? "tma16" : "red"), variant, gi_row0, ea / ma, eb / mb, good ? "OK" : "FAIL");
   cudaFree(dX); cudaFree(dGjT); cudaFree(dGiT); cudaFree(dA); cudaFree(dB);
   return good ? 0 : 1;
 }
 
-static void bench_fused_t(int n, int variant, int csplit) {
+static void bench_fused_t(int n, int variant, int csplit, int flush_mode = 2) {
   const int k = 64;
   size_t elems = (size_t)n * n;
   const long long ldt = ((n + 255) / 256) * 256 + 256;
@@ -392,12 +392,12 @@ static void bench_fused_t(int n, int variant, int csplit) {
   }
   CUtensorMap tr, tg, tb; std::string err;
   bool ok = make_tmap_bf16_2d(&tr, dX, n, n, n, 64, 256, &err) && make_tmap_bf16_2d(&tg, dGT, 128, ldt, ldt, 64, 128, &err) &&
-            make_tmap_generic(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dB, n, k, k, 16, 64, CU_TENSOR_MAP_SWIZZLE_NONE, &err);
+            make_tmap_generic(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dB, n, k, k, flush_mode == 2 ? 64 : 16, 64, CU_TENSOR_MAP_SWIZZLE_NONE, &err);
   if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
   CK(cudaFuncSetAttribute(umma_fused_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes));
   FusedTParams p;
   p.A = dA; p.B = dB; p.lda = k; p.ldb = k; p.GiT = dGT; p.ldt = ldt; p.n_rows = n; p.n_cols = n; p.k_a = k; p.k_b = k; p.gi_row0 = 0;
-  p.tma_flush = 1; p.variant = variant;
+  p.tma_flush = flush_mode; p.variant = variant;
   const int tiles = (n + 127) / 128;
   p.tiles_per_split = (tiles + csplit - 1) / csplit;
   const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
@@ -417,32 +417,35 @@ static void bench_fused_t(int n, int variant, int csplit) {
   for (int r = 0; r < reps; ++r) umma_fused_t_kernel<<<grid, kFtThreads, kFtSmemBytes>>>(tr, tg, tb, p);
   CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
   CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
-  printf("bench FUSED-T variant=%d n=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", variant, n, grid.x, grid.y,
+  printf("bench FUSED-T flush=%d variant=%d n=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", flush_mode, variant, n, grid.x, grid.y,
          ms, elems * 2.0 / 1e9 / (ms * 1e-3), 2.0 * 2.0 * elems * 128 / (ms * 1e-3) / 1e12);
   cudaFree(dX); cudaFree(dGT); cudaFree(dA); cudaFree(dB);
 }
 
 static int main_fused_t(int variant, int nbench) {
   int fails = 0;
-  fails += run_fused_t_case(256, 64, 64, 64, 1, 1, variant);
-  fails += run_fused_t_case(256, 256, 64, 64, 1, 1, variant);
-  fails += run_fused_t_case(512, 384, 64, 64, 1, 1, variant);
-  fails += run_fused_t_case(1000, 520, 64, 40, 1, 1, variant);
-  fails += run_fused_t_case(520, 1000, 50, 64, 3, 1, variant);
-  fails += run_fused_t_case(2048, 4096, 64, 64, 4, 1, variant);
+  fails += run_fused_t_case(256, 64, 64, 64, 1, 2, variant);
+  fails += run_fused_t_case(256, 256, 64, 64, 1, 2, variant);
+  fails += run_fused_t_case(512, 384, 64, 64, 1, 2, variant);
+  fails += run_fused_t_case(1000, 520, 64, 40, 1, 2, variant);
+  fails += run_fused_t_case(520, 1000, 50, 64, 3, 2, variant);
+  fails += run_fused_t_case(2048, 4096, 64, 64, 4, 2, variant);
   fails += run_fused_t_case(1000, 520, 64, 40, 1, 0, variant);
-  fails += run_fused_t_case(3000, 2100, 33, 36, 2, 1, variant);
-  fails += run_fused_t_case(777, 3001, 64, 64, 1, 1, variant);
-  fails += run_fused_t_case(777, 1001, 64, 64, 2, 1, variant, 1024);     // sharded: factor rows offset, 16-byte aligned
-  fails += run_fused_t_case(500, 1001, 64, 48, 1, 1, variant, 12500);    // sharded: offset not a multiple of 8 (scalar preload)
-  fails += run_fused_t_case(1000, 520, 64, 40, 1, 1, variant, 0, true);  // operand forms from split_factor_t
-  fails += run_fused_t_case(777, 1001, 20, 64, 2, 1, variant, 1024, true);
-  fails += run_fused_t_case(130, 77, 7, 12, 1, 1, variant);              // boxes larger than the tensors
-  fails += run_fused_t_case(300, 40, 64, 8, 1, 1, variant);
+  fails += run_fused_t_case(3000, 2100, 33, 36, 2, 2, variant);
+  fails += run_fused_t_case(777, 3001, 64, 64, 1, 2, variant);
+  fails += run_fused_t_case(777, 1001, 64, 64, 2, 2, variant, 1024);     // sharded: factor rows offset, 16-byte aligned
+  fails += run_fused_t_case(500, 1001, 64, 48, 1, 2, variant, 12500);    // sharded: offset not a multiple of 8 (scalar preload)
+  fails += run_fused_t_case(1000, 520, 64, 40, 1, 2, variant, 0, true);  // operand forms from split_factor_t
+  fails += run_fused_t_case(777, 1001, 20, 64, 2, 2, variant, 1024, true);
+  fails += run_fused_t_case(130, 77, 7, 12, 1, 2, variant);              // boxes larger than the tensors
+  fails += run_fused_t_case(300, 40, 64, 8, 1, 2, variant);
+  fails += run_fused_t_case(1000, 520, 64, 40, 1, 1, variant);           // per-warp 64-byte-row flush (mode 1)
+  fails += run_fused_t_case(2048, 4096, 64, 64, 4, 1, variant);
   printf("fusedT correctness (variant %d): %d failing cases\n", variant, fails);
   if (nbench > 0) {
     bench_fused_t(nbench, variant, 1);
-    bench_fused_t(nbench, variant | 16, 1);   // no staggered sweep
+    bench_fused_t(nbench, variant, 1, 1);     // per-warp flush
+    bench_fused_t(nbench, variant | 16, 1);   // staggered sweep
     bench_fused_t(nbench, variant | 8, 1);    // no flush
     bench_fused_t(nbench, variant | 2, 1);    // no B^T-product
     bench_fused_t(nbench, variant | 4, 1);    // no A^T-product
@@ -456,8 +459,10 @@ int main(int argc, char** argv) {
     const int n = argc > 2 ? atoi(argv[2]) : 37888;
     g_sustain_s = argc > 3 ? atof(argv[3]) : 4.0;
     printf("sustained mode: %.1f s per configuration (second half timed)\n", g_sustain_s);
-    for (int mode : {0, 2, 4, 6, 7}) bench_fused(n, mode);            // v3: full, no B MMA, no A MMA, no MMA, TMA only
-    for (int v : {0, 2, 4, 6, 14}) bench_fused_t(n, v, 1);            // v4: same
+    if (argc > 4) for (int mode : {0, 2, 4, 6, 7}) bench_fused(n, mode);   // v3: full, no B MMA, no A MMA, no MMA, TMA only
+    for (int mode : {0, 1}) bench_fused(n, mode);                         // v3: full, no flush
+    for (int v : {0, 16, 8}) bench_fused_t(n, v, 1, 2);                   // v4, one 16 KB reduce per chunk: plain, staggered sweep, no flush
+    bench_fused_t(n, 0, 1, 1);                                           // v4, per-warp 64-byte-row reduces
     return 0;
   }
   if (argc > 1 && argv[1][0] == 't') return main_fused_t(argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atoi(argv[3]) : 0);

@@ -275,7 +275,7 @@ class Engine : public EngineBase {
     bool has_backbone = false;
     CUtensorMap tmX, tmXT, tmEs, tmB;
     bool has_tmB = false;
-    CUtensorMap tmX256, tmB16;   // fused kernel v4: relation box {64 cols, 256 rows}; B box {16 cols, 64 rows}, no swizzle
+    CUtensorMap tmX256, tmB16;   // fused kernel v4: relation box {64 cols, 256 rows}; B box {64 cols, 64 rows}, no swizzle
     bool has_tmB16 = false, v4_ok = false;
   };
 
@@ -509,9 +509,9 @@ class Engine : public EngineBase {
         if (fused_ver_ == 4 && kDT == FZ_F32 && r.rows_loc >= 256 && r.cols >= 64 && Ti.GsT.p != nullptr && Tj.GsT.p != nullptr) {
           r.v4_ok = make_tmap_2d(&r.tmX256, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols,
                                  (uint64_t)r.ld, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B, &e);
-          if (r.v4_ok && (Ti.k % 4) == 0 && Ti.k >= 16 && Tj.n_pad >= 64)
+          if (r.v4_ok && (Ti.k % 4) == 0 && Tj.n_pad >= 64)      // one {64 k, 64 rows} reduce per chunk (flush mode 2)
             r.has_tmB16 = make_tmap_2d(&r.tmB16, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, r.B.p, (uint64_t)Tj.n_pad, (uint64_t)Ti.k,
-                                       (uint64_t)Ti.k, 16, 64, CU_TENSOR_MAP_SWIZZLE_NONE, &e);
+                                       (uint64_t)Ti.k, 64, 64, CU_TENSOR_MAP_SWIZZLE_NONE, &e);
         }
       }
     }
@@ -1305,7 +1305,7 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
     q.ldt = Ti.ldt;
     q.n_rows = p.n_rows; q.n_cols = p.n_cols; q.k_a = p.k_a; q.k_b = p.k_b; q.gi_row0 = p.gi_row0;
     q.tiles_per_split = p.tiles_per_split; q.a_atomic = p.a_atomic;
-    q.tma_flush = r.has_tmB16 ? 1 : 0;
+    q.tma_flush = r.has_tmB16 ? 2 : 0;
     q.variant = 0;
     umma_fused_t_kernel<<<grid, kFtThreads, kFtSmemBytes, st>>>(r.tmX256, Tj.tmGT, r.has_tmB16 ? r.tmB16 : r.tmX256, q);
   } else {

@@ -114,6 +114,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 __device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the shared-memory sources of all committed bulk groups have been read (buffers reusable)
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// same, but up to kPending of the most recent groups may still be reading
+template <int kPending>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
+// bar.sync among `threads` threads (a multiple of 32) on named barrier `id` (1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 // wait until all committed bulk groups have fully completed (global writes performed)
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 

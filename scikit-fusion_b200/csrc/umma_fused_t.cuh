@@ -43,10 +43,11 @@ struct FusedTParams {
   int gi_row0;                    // column of GiT that pairs with local row 0 of R (row-sharded factors)
   int tiles_per_split;            // 128-column tiles handled per blockIdx.y (same unit as the v3 kernel)
   int a_atomic;                   // 1: several column splits add into A (caller zeroes A), 0: plain store
-  int tma_flush;                  // 1: B partials go out as TMA reduce-add (needs tmB); 0: red.global fallback
+  int tma_flush;                  // B partials: 2 = ONE TMA reduce-add of 64 rows x 256 B per chunk and CTA (tmB box {64, 64}),
+                                  // 1 = one of 64 rows x 64 B per warp (tmB box {16, 64}), 0 = red.global fallback
   int variant;                    // developer probe: bit0 = swap the bf16 halves of the TMEM A-operand words,
                                   //                  bit1 = skip B^T-product, bit2 = skip A^T-product, bit3 = skip flush,
-                                  //                  bit4 = no staggered sweep
+                                  //                  bit4 = staggered sweep, bit5 = no GsT_j reloads (wrong results: L2->SM traffic study)
 };
 
 constexpr int kFtThreads = 192;   // warp 0: TMA producer | 1: MMA issuer | 2..5: epilogue
@@ -56,7 +57,7 @@ constexpr int kFtStages = 4;
 constexpr int kFtRBytes = kFtRows * kFtChunk * 2;         // 32 KB
 constexpr int kFtGBytes = 128 * kFtChunk * 2;             // 16 KB
 constexpr int kFtStageBytes = kFtRBytes + kFtGBytes;      // 48 KB
-constexpr int kFtFlushBytes = 4 * 4096;                   // 4 warps x (64 rows x 16 fp32)
+constexpr int kFtFlushBytes = 2 * 16384;                  // two staging buffers of 64 rows x 64 fp32 (flush mode 2), or 4 warps x 4 KB (mode 1)
 constexpr int kFtSmemBytes = kFtStages * kFtStageBytes + kFtFlushBytes + 1024 + 256;
 
 namespace ptx {
@@ -112,10 +113,11 @@ umma_fused_t_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf1
   const int chunk_begin = blockIdx.y * p.tiles_per_split * 2;
   const int chunk_end = min(total_chunks, chunk_begin + p.tiles_per_split * 2);
   const int n_chunks = max(0, chunk_end - chunk_begin);
-  // Staggered sweep: CTA x starts its column sweep at a different chunk (and wraps around), so that at any moment the
-  // CTAs reduce their B partials into DIFFERENT rows of B (L2 reductions serialise per address) and pull different
-  // GsT_j tiles.  variant bit4 switches it off (developer probe).
-  const int shift = (p.variant & 16) || n_chunks == 0 ? 0 : (int)(((long long)blockIdx.x * n_chunks) / gridDim.x);
+  // Optional staggered sweep (variant bit4): CTA x starts its column sweep at a different chunk and wraps around, so that
+  // at any moment the CTAs reduce their B partials into different rows of B.  +1.6 % in a burst, but the GsT_j tiles are
+  // then no longer shared in L2 at the same time (DRAM traffic 1.09x instead of 1.02x) and under the power cap it is
+  // 2-3 % slower (profiles/r01b_sustained_v4_flush_study.log): off by default.
+  const int shift = !(p.variant & 16) || n_chunks == 0 ? 0 : (int)(((long long)blockIdx.x * n_chunks) / gridDim.x);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmR);
@@ -145,10 +147,11 @@ umma_fused_t_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf1
       const int col0 = (chunk_begin + cc) * kFtChunk;
       ptx::mbar_wait_wd(&empty[s], ((c / kFtStages) & 1) ^ 1);
       if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(&full[s], kFtStageBytes);
+        const bool load_g = !(p.variant & 32) || c < kFtStages;     // probe bit5: factor chunks loaded once, then reused
+        ptx::mbar_expect_tx(&full[s], load_g ? kFtStageBytes : kFtRBytes);
         uint8_t* dst = st_base + s * kFtStageBytes;
         ptx::tma_load_2d(dst, &tmR, &full[s], col0, r0, ptx::kEvictFirst);
-        ptx::tma_load_2d(dst + kFtRBytes, &tmGjT, &full[s], col0, 0, ptx::kEvictLast);
+        if (load_g) ptx::tma_load_2d(dst + kFtRBytes, &tmGjT, &full[s], col0, 0, ptx::kEvictLast);
       }
       __syncwarp();
     }
@@ -241,7 +244,7 @@ umma_fused_t_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf1
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bacc_empty[h]);                             // D_B[h] may be overwritten
-      if (quarter * 16 >= p.k_b || skip_flush) continue;
+      if (skip_flush || (p.tma_flush != 2 && quarter * 16 >= p.k_b)) continue;   // (mode 2: every warp joins the barriers)
       // pair sum: the hi lane keeps even columns, the lo lane odd ones; y[q] belongs to column 2 q + half
       float y[32];
 #pragma unroll
@@ -252,7 +255,21 @@ umma_fused_t_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf1
       }
       const int cc = c + shift < n_chunks ? c + shift : c + shift - n_chunks;
       const int col0 = (chunk_begin + cc) * kFtChunk;               // first B row (column of R) of this chunk
-      if (p.tma_flush) {
+      if (p.tma_flush == 2) {
+        // CTA-wide staging buffer [64 cols][64 k] fp32 (double-buffered), one 16 KB reduce-add per chunk: 256-byte rows
+        // instead of four 64-byte-row operations (fewer TMA / L2 requests per flushed byte)
+        float* stage = reinterpret_cast<float*>(fl_st + (c & 1) * 16384);
+        if (warp == 2 && ptx::elect_one()) ptx::tma_wait_read<1>();   // the reduce issued two chunks ago has read this buffer
+        ptx::named_barrier_sync(1, 128);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) stage[(2 * q + half) * 64 + kcol] = y[q];
+        ptx::fence_proxy_async();
+        ptx::named_barrier_sync(2, 128);
+        if (warp == 2 && ptx::elect_one()) {
+          ptx::tma_reduce_add_2d(&tmB, stage, 0, col0);             // rows / columns beyond the tensor are clipped
+          ptx::tma_commit_group();
+        }
+      } else if (p.tma_flush) {
         if (staged) {                                               // previous reduce has read the staging buffer
           if (ptx::elect_one()) ptx::tma_wait_read_all();           // (elect.sync is deterministic: always the same lane)
           __syncwarp();
