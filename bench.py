@@ -103,6 +103,17 @@ class ClockSampler(threading.Thread):
             self.sample()
             time.sleep(0.1)
 
+    def sample_instant_power(self):
+        """power.draw is a ~1 s moving average and lags a sub-second timed region; newer drivers also expose the
+        instantaneous reading.  Optional: an unknown field just leaves it out."""
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=power.draw.instant",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+            if out.returncode == 0:
+                self.instant_w = float(out.stdout.strip().split()[0])
+        except Exception:
+            pass
+
     def summary(self):
         sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
@@ -119,6 +130,7 @@ class ClockSampler(threading.Thread):
         power, limit = num(6), num(7)
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm), "power_w": round(max(power), 1) if power else None,
+                "power_instant_w": getattr(self, "instant_w", None),
                 "power_limit_w": round(max(limit), 1) if limit else None}
 
 
@@ -189,6 +201,8 @@ def gpu_arm(args):
     e0.record()
     fzd.run_iterations(shard, coll, args.steps)
     e1.record()
+    if rank == 0:
+        sampler.sample_instant_power()   # the host has only enqueued the steps: the GPU is in the middle of the timed region
     barrier()
     sampler.stop_flag = True
     if rank == 0 and not sampler.rows:     # timed region shorter than one nvidia-smi round trip: sample right after it
