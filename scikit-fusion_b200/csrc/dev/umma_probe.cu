@@ -237,7 +237,7 @@ static void bench_fused(int n, int skip_flush) {
   for (int csplit : {1}) {
     FusedParams p;
     p.A = dA; p.B = dB; p.lda = k; p.ldb = k; p.n_rows = n; p.n_cols = n; p.k_a = k; p.k_b = k; p.gi_row0 = 0;
-    p.probe_skip_flush = skip_flush & 7; p.tma_flush = (skip_flush & 8) ? 0 : 1;
+    p.probe_skip_flush = skip_flush & 0x37; p.tma_flush = (skip_flush & 8) ? 0 : 1;
     const int tiles = (n + 127) / 128;
     p.tiles_per_split = (tiles + csplit - 1) / csplit;
     const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
@@ -258,7 +258,7 @@ static void bench_fused(int n, int skip_flush) {
     for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, p);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
-    printf("bench FUSED%s n=%d csplit=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", skip_flush == 0 ? " (tma flush)" : skip_flush == 8 ? " (red flush)" : (skip_flush == 1 ? " (probe: no RED)" : (skip_flush == 2 ? " (probe: no B MMA)" : (skip_flush == 4 ? " (probe: no A MMA)" : (skip_flush == 3 ? " (probe: no RED, no B MMA)" : (skip_flush == 6 ? " (probe: no MMA, flush on)" : " (probe: TMA only)"))))), n, splits, grid.x, grid.y,
+    printf("bench FUSED%s n=%d csplit=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", skip_flush == 0 ? " (tma flush)" : skip_flush == 8 ? " (red flush)" : (skip_flush == 1 ? " (probe: no RED)" : (skip_flush == 2 ? " (probe: no B MMA)" : (skip_flush == 4 ? " (probe: no A MMA)" : (skip_flush == 3 ? " (probe: no RED, no B MMA)" : (skip_flush == 6 ? " (probe: no MMA, flush on)" : (skip_flush == 16 ? " (probe: B-product 1 term)" : (skip_flush == 48 ? " (probe: both products 1 term)" : " (probe: TMA only)"))))))), n, splits, grid.x, grid.y,
            ms, elems * 2.0 / 1e9 / (ms * 1e-3), 2.0 * 2.0 * elems * N / (ms * 1e-3) / 1e12);
   }
   cudaFree(dX); cudaFree(dG); cudaFree(dA); cudaFree(dB);
@@ -460,7 +460,7 @@ int main(int argc, char** argv) {
     g_sustain_s = argc > 3 ? atof(argv[3]) : 4.0;
     printf("sustained mode: %.1f s per configuration (second half timed)\n", g_sustain_s);
     if (argc > 4) for (int mode : {0, 2, 4, 6, 7}) bench_fused(n, mode);   // v3: full, no B MMA, no A MMA, no MMA, TMA only
-    for (int mode : {0, 1}) bench_fused(n, mode);                         // v3: full, no flush
+    for (int mode : {0, 16, 48, 1}) bench_fused(n, mode);                 // v3: full, B 1 term, A and B 1 term, no flush
     for (int v : {0, 16, 8}) bench_fused_t(n, v, 1, 2);                   // v4, one 16 KB reduce per chunk: plain, staggered sweep, no flush
     bench_fused_t(n, 0, 1, 1);                                           // v4, per-warp 64-byte-row reduces
     return 0;

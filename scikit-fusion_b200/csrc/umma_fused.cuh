@@ -35,7 +35,9 @@ struct FusedParams {
   int tiles_per_split; // column tiles handled per blockIdx.y
   int a_atomic;        // 1: several column splits add into A (caller zeroes A), 0: plain store
   int tma_flush;       // 1: B partials go out as TMA reduce-add (needs tmB); 0: red.global fallback
-  int probe_skip_flush;// developer probe only (wrong results): bit0 = no reductions, bit1 = no B-product MMAs, bit2 = no A-product MMAs
+  int probe_skip_flush;// developer probe only (wrong results): bit0 = no reductions, bit1 = no B-product MMAs, bit2 = no A-product MMAs,
+                       // bit4 = B-product with the first split term only (N = 64), bit5 = A-product likewise: what a 1.5- / 1-term
+                       // operand form would cost (profiles/r01b_sustained_term_count_study.log)
 };
 
 constexpr int kFuThreads = 224;   // warp 0: R producer | 1: MMA | 2..5: epilogue | 6: Gs producer
@@ -148,8 +150,8 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
     // (whole warp converged, one elected lane issues -- see the producer note above: this removes ~100 cycles of
     //  waterfall-loop overhead per tcgen05.mma, which at 16 MMAs per tile was the kernel's actual bound)
     if (n_tiles > 0) {
-      constexpr uint32_t idesc_a = ptx::idesc_bf16_f32(128, 128, false, true);   // R K-major  x Gs MN-major
-      constexpr uint32_t idesc_b = ptx::idesc_bf16_f32(128, 128, true, true);    // R^T MN-major x Gs MN-major
+      const uint32_t idesc_a = ptx::idesc_bf16_f32(128, (p.probe_skip_flush & 32) ? 64 : 128, false, true);   // R K-major  x Gs MN-major
+      const uint32_t idesc_b = ptx::idesc_bf16_f32(128, (p.probe_skip_flush & 16) ? 64 : 128, true, true);    // R^T MN-major x Gs MN-major
       const bool do_a = !(p.probe_skip_flush & 4), do_b = !(p.probe_skip_flush & 2);
       const uint32_t r_base = ptx::smem_u32(r_st), gj_base = ptx::smem_u32(gj_st);
       const uint32_t gi0 = ptx::smem_u32(gi_st), gi1 = gi0 + kFuTileBytes;

@@ -158,3 +158,20 @@ def test_transform_seeded_on_the_device_follows_the_oracle(init_type):
             got = solver.transform(R_new, {}, tags[0], rk, G, S, max_iter=iters, init_type=init_type,
                                    random_state=np.random.RandomState(3), dtype="float64", device_init=True)
             assert rel_fro(ref, got) < 1e-9, (iters, rel_fro(ref, got))
+
+
+def test_where_the_data_driven_seed_is_computed():
+    """options.device_init: 'auto' keeps the reference-exact numpy path for small host graphs."""
+    from skfusion.fusion import solver
+    from skfusion.fusion.options import resolve, AUTO_FP64_MAX_ENTRIES
+    small = {("a", "b"): [np.zeros((10, 12))]}
+
+    class Big(object):                 # shape-only stand-in: the decision never touches the data
+        shape = (AUTO_FP64_MAX_ENTRIES // 1000 + 1, 1000)
+
+    assert solver._init_on_device(resolve(n_entries=120), "random_c", small, {}) is False
+    assert solver._init_on_device(resolve(n_entries=120), "random", small, {}) is False
+    assert solver._init_on_device(resolve(n_entries=120, device_init=True), "random_vcol", small, {}) is True
+    assert solver._init_on_device(resolve(n_entries=120, device_init=True), "random", small, {}) is False
+    assert solver._init_on_device(resolve(n_entries=None), "random_c", {("a", "b"): [Big()]}, {}) is True
+    assert solver._init_on_device(resolve(n_entries=None, device_init=False), "random_c", {("a", "b"): [Big()]}, {}) is False
