@@ -2,6 +2,7 @@
 // double-precision reference for every operand-layout variant, then times them on a large matrix.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o umma_probe umma_probe.cu
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -153,7 +154,7 @@ static void bench(int n, int terms, bool trans) {
 }
 
 // ---- fused single-pass kernel: A = X Gj, B = X^T Gi from one stream of X
-static int run_fused_case(int rows, int cols, int ka, int kb, int csplit, int tma_flush = 1) {
+static int run_fused_case(int rows, int cols, int ka, int kb, int csplit, int tma_flush = 1, int b_terms = 2) {
   const int kp = 64, N = 128;
   const int ld = (cols + 7) / 8 * 8;
   std::vector<__nv_bfloat16> hX((size_t)rows * ld), hGj((size_t)cols * N), hGi((size_t)rows * N);
@@ -170,6 +171,9 @@ static int run_fused_case(int rows, int cols, int ka, int kb, int csplit, int tm
   };
   fillG(hGj, fGj, cols, ka);
   fillG(hGi, fGi, rows, kb);
+  if (b_terms == 1)
+    for (int r = 0; r < rows; ++r)
+      for (int q = 0; q < kp; ++q) fGi[(size_t)r * N + kp + q] = 0.f;   // the reference ignores the second term too
   __nv_bfloat16 *dX, *dGj, *dGi; float *dA, *dB;
   CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dGj, hGj.size() * 2)); CK(cudaMalloc(&dGi, hGi.size() * 2));
   CK(cudaMalloc(&dA, (size_t)rows * ka * 4)); CK(cudaMalloc(&dB, (size_t)cols * kb * 4));
@@ -185,7 +189,7 @@ static int run_fused_case(int rows, int cols, int ka, int kb, int csplit, int tm
   if (!tma_flush) tb = tr;
   if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
   FusedParams p;
-  p.A = dA; p.B = dB; p.lda = ka; p.ldb = kb; p.n_rows = rows; p.n_cols = cols; p.k_a = ka; p.k_b = kb; p.gi_row0 = 0; p.probe_skip_flush = 0; p.tma_flush = tma_flush;
+  p.A = dA; p.B = dB; p.lda = ka; p.ldb = kb; p.n_rows = rows; p.n_cols = cols; p.k_a = ka; p.k_b = kb; p.gi_row0 = 0; p.probe_skip_flush = 0; p.tma_flush = tma_flush; p.b_terms = b_terms;
   const int tiles = (cols + 127) / 128;
   p.tiles_per_split = (tiles + csplit - 1) / csplit;
   const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
@@ -212,8 +216,8 @@ static int run_fused_case(int rows, int cols, int ka, int kb, int csplit, int tm
       mb = fmax(mb, fabs(s)); eb = fmax(eb, fabs(s - hB[(size_t)c * kb + q]));
     }
   const bool good = ea / ma < 2e-5 && eb / mb < 2e-5;
-  printf("fused rows=%d cols=%d ka=%d kb=%d csplit=%d flush=%s : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb, splits,
-         tma_flush ? "tma" : "red", ea / ma, eb / mb, good ? "OK" : "FAIL");
+  printf("fused rows=%d cols=%d ka=%d kb=%d csplit=%d flush=%s b_terms=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb, splits,
+         tma_flush ? "tma" : "red", b_terms, ea / ma, eb / mb, good ? "OK" : "FAIL");
   cudaFree(dX); cudaFree(dGj); cudaFree(dGi); cudaFree(dA); cudaFree(dB);
   return good ? 0 : 1;
 }
@@ -237,7 +241,7 @@ static void bench_fused(int n, int skip_flush) {
   for (int csplit : {1}) {
     FusedParams p;
     p.A = dA; p.B = dB; p.lda = k; p.ldb = k; p.n_rows = n; p.n_cols = n; p.k_a = k; p.k_b = k; p.gi_row0 = 0;
-    p.probe_skip_flush = skip_flush & 0x37; p.tma_flush = (skip_flush & 8) ? 0 : 1;
+    p.probe_skip_flush = skip_flush & 0x37; p.tma_flush = (skip_flush & 8) ? 0 : 1; p.b_terms = 2;
     const int tiles = (n + 127) / 128;
     p.tiles_per_split = (tiles + csplit - 1) / csplit;
     const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
@@ -455,6 +459,15 @@ static int main_fused_t(int variant, int nbench) {
 }
 
 int main(int argc, char** argv) {
+  setvbuf(stdout, nullptr, _IONBF, 0);
+  if (argc > 1 && argv[1][0] == 'm') {   // single-term B-product (the fp16 variant of this probe hit an illegal instruction:
+    int fails = 0;                       //  bf16 A x fp16 B is not a legal kind::f16 combination, profiles/r01b_mixed_format_probe.log)
+    fails += run_fused_case(512, 384, 64, 64, 1, 1, 1);
+    fails += run_fused_case(1000, 520, 64, 40, 1, 1, 1);
+    fails += run_fused_case(2048, 4096, 64, 64, 4, 1, 1);
+    printf("single-term B-product probe: %d failing cases\n", fails);
+    return fails ? 1 : 0;
+  }
   if (argc > 1 && argv[1][0] == 's') {   // sustained (power-capped) component study:  s <n> <seconds>
     const int n = argc > 2 ? atoi(argv[2]) : 37888;
     g_sustain_s = argc > 3 ? atof(argv[3]) : 4.0;

@@ -1270,6 +1270,7 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   p.k_b = Ti.k;
   p.gi_row0 = (int)Ti.row0;
   p.probe_skip_flush = 0;
+  p.b_terms = 2;
   p.tma_flush = r.has_tmB ? 1 : 0;
   const int pairs = (int)((r.rows_loc + 2 * kFuTile - 1) / (2 * kFuTile));
   const int tiles = (int)((r.cols + kFuTile - 1) / kFuTile);

@@ -35,6 +35,9 @@ struct FusedParams {
   int tiles_per_split; // column tiles handled per blockIdx.y
   int a_atomic;        // 1: several column splits add into A (caller zeroes A), 0: plain store
   int tma_flush;       // 1: B partials go out as TMA reduce-add (needs tmB); 0: red.global fallback
+  int b_terms;         // split terms multiplied in the B-product: 2 (default) or 1 = first term only (N = 64; validated, unused by
+                       // the engine: see DESIGN.md section 4).  An fp16 first term is NOT possible: kind::f16 with a bf16 A operand
+                       // and an fp16 B operand raises an illegal-instruction exception on sm_100a (profiles/r01b_mixed_format_probe.log)
   int probe_skip_flush;// developer probe only (wrong results): bit0 = no reductions, bit1 = no B-product MMAs, bit2 = no A-product MMAs,
                        // bit4 = B-product with the first split term only (N = 64), bit5 = A-product likewise: what a 1.5- / 1-term
                        // operand form would cost (profiles/r01b_sustained_term_count_study.log)
@@ -151,7 +154,7 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
     //  waterfall-loop overhead per tcgen05.mma, which at 16 MMAs per tile was the kernel's actual bound)
     if (n_tiles > 0) {
       const uint32_t idesc_a = ptx::idesc_bf16_f32(128, (p.probe_skip_flush & 32) ? 64 : 128, false, true);   // R K-major  x Gs MN-major
-      const uint32_t idesc_b = ptx::idesc_bf16_f32(128, (p.probe_skip_flush & 16) ? 64 : 128, true, true);    // R^T MN-major x Gs MN-major
+      const uint32_t idesc_b = ptx::idesc_bf16_f32(128, ((p.probe_skip_flush & 16) || p.b_terms == 1) ? 64 : 128, true, true);   // R^T MN-major x Gs MN-major
       const bool do_a = !(p.probe_skip_flush & 4), do_b = !(p.probe_skip_flush & 2);
       const uint32_t r_base = ptx::smem_u32(r_st), gj_base = ptx::smem_u32(gj_st);
       const uint32_t gi0 = ptx::smem_u32(gi_st), gi1 = gi0 + kFuTileBytes;
@@ -248,6 +251,10 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
         ptx::tmem_ld32(lane_addr + 256 + gs * 128 + q0, hi);
         ptx::tmem_ld32(lane_addr + 256 + gs * 128 + 64 + q0, lo);
         ptx::tmem_ld_wait();
+        if (p.b_terms == 1) {                                      // single-term B-product: the lo half was never written
+#pragma unroll
+          for (int i = 0; i < 32; ++i) lo[i] = 0.f;
+        }
         if (q0 == 32) {             // all TMEM reads of this buffer are done: hand it back to the MMA warp
           ptx::tc_fence_before();
           ptx::mbar_arrive(&bacc_empty[gs]);
