@@ -532,8 +532,10 @@ def main():
             "value": c["value"], "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / c["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "5 object types x n=%d objects, 10 relations, rank 64 (CPU arm measured on a bounded sample)" % n,
-                       "n_per_type": n, "rank": RANK, "relations": len(PAIRS)},
+            "config": {"workload": "5 object types x n=%d objects, 10 relations (all pairs i<j) n x n stored bf16, rank 64, "
+                                   "init 'random' -- the same graph as the GPU arm; CPU arm: float64 oracle port of the reference's "
+                                   "numpy path on all host cores, measured on a bounded sample and extrapolated (see cpu_baseline.sample)" % n,
+                       "n_per_type": n, "rank": RANK, "relations": len(PAIRS), "relation_bytes_total": 10 * n * n * 2},
             "cpu_baseline": {"value": c["value"], "unit": "it/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]},
             "e2e": {"value": c["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
