@@ -67,7 +67,9 @@ def cpu_arm(n_workload, n_sample, steps, warmup):
         per_it = np.diff(stamps)[max(0, warmup - 1):]
         return float(np.median(per_it)), len(per_it)
 
-    n_half = max(256, n_sample // 2)
+    n_half = max(64, n_sample // 2)
+    if n_half >= n_sample:
+        n_half = max(1, n_sample // 2)
     t_half, _ = timed(n_half)
     t_full, count = timed(n_sample)
     a = (t_full - t_half) / (float(n_sample) ** 2 - float(n_half) ** 2)
