@@ -86,3 +86,30 @@ def test_host_layer_matches_reference_estimators_in_process():
     for a, b in zip(rels_ref, rels_own):
         assert rel_fro(f_ref.backbone(a), f_own.backbone(b)) < 1e-11
         assert rel_fro(f_ref.complete(a), f_own.complete(b)) < 1e-11
+
+
+@pytest.mark.parametrize("mode", ["mean", "row_mean", "col_mean", "const"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_fill_functions_equal_the_reference(mode, masked):
+    """Relation.filled(): our host fill functions against the reference's (fusion_graph.py:464-510) on NaN / masked data.
+    The device fill (fz_fill_unknown) is checked against ours in tests/test_device_preprocessing.py, which closes the chain."""
+    from skfusion.fusion import graph as mine
+    theirs = ref.load()
+    import importlib
+    fg = importlib.import_module(theirs.FusionGraph.__module__)
+    rs = np.random.RandomState(3)
+    x = rs.rand(23, 17) * 5 - 1
+    x[rs.rand(23, 17) < 0.2] = np.nan
+    x[4, :] = np.nan
+    if masked:
+        x = np.ma.masked_array(np.nan_to_num(x, nan=7.0), mask=np.isnan(x) | (rs.rand(23, 17) < 0.1))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if mode == "const":
+            want, got = fg.fill_const(x, 0.5), mine.fill_const(x, 0.5)
+        else:
+            want, got = fg.FILL_TYPE[mode](x), mine.FILL_TYPE[mode](x)
+    assert np.ma.is_masked(want) == np.ma.is_masked(got)
+    np.testing.assert_array_equal(np.ma.getdata(want), np.ma.getdata(got))
+    if np.ma.is_masked(want):
+        np.testing.assert_array_equal(np.ma.getmaskarray(want), np.ma.getmaskarray(got))
