@@ -113,3 +113,55 @@ def test_fill_functions_equal_the_reference(mode, masked):
     np.testing.assert_array_equal(np.ma.getdata(want), np.ma.getdata(got))
     if np.ma.is_masked(want):
         np.testing.assert_array_equal(np.ma.getmaskarray(want), np.ma.getmaskarray(got))
+
+
+def _strip_engine_kwargs(fn):
+    return lambda **kw: fn(**{k: v for k, v in kw.items() if k not in ("device", "dtype", "storage", "split_terms", "device_init")})
+
+
+def test_host_layer_matches_reference_dfmc_and_transform_in_process():
+    """Estimator level, same process: Dfmc with masked entries and two fill modes, then DfmfTransform of new
+    rows against the fitted model -- marshalling (filled / preprocessor / mask survival, dfmc.py:69-94; dfmf.py:175-189),
+    RNG order and accessors must match the reference's classes when the oracle stands in for the engine."""
+    import skfusion.fusion as mine
+    from skfusion.fusion import solver
+    theirs = ref.load()
+    rs = np.random.RandomState(1)
+    R12 = np.ma.masked_array(rs.rand(40, 30), mask=rs.rand(40, 30) < 0.25)
+    R13 = rs.rand(40, 25)
+    R13[rs.rand(40, 25) < 0.1] = np.nan
+    R23 = rs.rand(30, 25)
+    T1 = (rs.rand(40, 40) < 0.1) * -0.05
+    T1 = (T1 + T1.T) / 2
+    R12_new, R13_new = rs.rand(12, 30), rs.rand(12, 25)
+
+    def build(mod):
+        t1, t2, t3 = mod.ObjectType('type1', 6), mod.ObjectType('type2', 5), mod.ObjectType('type3', 4)
+        rels = [mod.Relation(R12.copy(), t1, t2), mod.Relation(R13.copy(), t1, t3, fill_value='row_mean'),
+                mod.Relation(R23.copy(), t2, t3, preprocessor=lambda x: x * 2.0, postprocessor=lambda x: x / 2.0),
+                mod.Relation(T1.copy(), t1, t1)]
+        new = [mod.Relation(R12_new.copy(), t1, t2), mod.Relation(R13_new.copy(), t1, t3)]
+        return mod.FusionGraph(rels), mod.FusionGraph(new), (t1, t2, t3), rels
+
+    out = {}
+    saved = (solver.dfmc, solver.transform)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, mod in (("ref", theirs), ("own", mine)):
+            g, g_new, types, rels = build(mod)
+            if name == "own":
+                solver.dfmc, solver.transform = _strip_engine_kwargs(oracle.dfmc), _strip_engine_kwargs(oracle.transform)
+            try:
+                fuser = mod.Dfmc(max_iter=12, init_type='random_vcol', random_state=3).fuse(g)
+                tr = mod.DfmfTransform(max_iter=15, random_state=5).transform(types[0], g_new, fuser)
+            finally:
+                solver.dfmc, solver.transform = saved
+            out[name] = ([fuser.factor(t) for t in types], [fuser.backbone(r) for r in rels[:3]],
+                         [fuser.complete(r) for r in rels[:3]], tr.factor(types[0]))
+    for a, b in zip(out["ref"][0], out["own"][0]):
+        assert rel_fro(a, b) < 1e-11
+    for a, b in zip(out["ref"][1], out["own"][1]):
+        assert rel_fro(a, b) < 1e-10
+    for a, b in zip(out["ref"][2], out["own"][2]):
+        assert rel_fro(a, b) < 1e-10
+    assert rel_fro(out["ref"][3], out["own"][3]) < 1e-11

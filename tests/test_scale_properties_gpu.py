@@ -67,7 +67,7 @@ def test_streamed_product_code_paths_agree(env):
     Ga, Sa = _fit(R, types, ranks, 6, dtype="float32", storage="bfloat16")
     Gb, Sb = _fit(R, types, ranks, 6, env=env, dtype="float32", storage="bfloat16")
     g, s = _worst(Ga, Sa, Gb, Sb)
-    assert g < 2e-5 and s < 2e-4, (g, s)           # same arithmetic, different summation orders (fp32)
+    assert g < 1e-4 and s < 1e-3, (g, s)           # same arithmetic, different summation orders (fp32); path tolerance is 1e-3 / 5e-3
 
 
 def test_scale_covariance_on_the_100k_node_graph():
@@ -81,7 +81,7 @@ def test_scale_covariance_on_the_100k_node_graph():
     G4, S4 = _fit(R, types, ranks, 4, dtype="float32", storage="bfloat16")
     S4 = {k: [m / 4.0 for m in v] for k, v in S4.items()}
     g, s = _worst(G1, S1, G4, S4)
-    assert g < 1e-5 and s < 1e-4, (g, s)
+    assert g < 5e-5 and s < 5e-4, (g, s)           # only the order of the L2 reductions differs between the two fits
     for k in G1:
         assert np.isfinite(G1[k]).all() and (G1[k] >= 0).all()
 
@@ -124,7 +124,7 @@ def test_permutation_equivariance():
     G0p = dict(G0)
     G0p[1] = G0[1][perm]
     Gp, Sp = run(Rp, G0p)
-    assert rel_fro(G[1][perm], Gp[1]) < 1e-5
-    assert rel_fro(G[0], Gp[0]) < 1e-5 and rel_fro(G[2], Gp[2]) < 1e-5
+    assert rel_fro(G[1][perm], Gp[1]) < 5e-5
+    assert rel_fro(G[0], Gp[0]) < 5e-5 and rel_fro(G[2], Gp[2]) < 5e-5
     for key in S:
-        assert rel_fro(S[key], Sp[key]) < 1e-4
+        assert rel_fro(S[key], Sp[key]) < 5e-4
