@@ -857,6 +857,8 @@ class Engine : public EngineBase {
     if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "device initialisation on sharded handles is not implemented");
     RelRec& r = relation(rel);
     if (r.theta) FZ_THROW(FZ_ERR_INVALID, "constraint matrices do not seed factors");
+    if (axis != 0 && axis != 1) FZ_THROW(FZ_ERR_INVALID, "axis must be 0 (column norms) or 1 (row norms)");
+    if (dst_host == nullptr) FZ_THROW(FZ_ERR_INVALID, "null destination");
     const int64_t count = axis == 0 ? r.cols : r.rows_loc;
     DevBuf out;
     out.alloc((size_t)std::max<int64_t>(1, count) * 8);
@@ -889,7 +891,7 @@ class Engine : public EngineBase {
     if (t < 0 || t >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id %d", t);
     RelRec& r = relation(rel);
     if (r.theta || (r.ti != t && r.tj != t)) FZ_THROW(FZ_ERR_INVALID, "relation %d does not touch type %d", rel, t);
-    if (p_c < 0) FZ_THROW(FZ_ERR_INVALID, "negative sample size");
+    if (p_c < 0 || (p_c > 0 && idx_host == nullptr)) FZ_THROW(FZ_ERR_INVALID, "bad sample plan");
     TypeRec& Tt = *types_[t];
     const bool row_role = (r.ti == t);
     TypeRec& To = row_role ? *types_[r.tj] : *types_[r.ti];     // the type the sampled columns index
