@@ -126,10 +126,12 @@ class Relation(object):
         """A copy of the data with unknown values replaced according to ``fill_value``.  Device-resident data (a torch
         CUDA tensor) is copied and filled on the GPU (fz_fill_unknown); it never visits the host."""
         if _is_device_tensor(self.data):
+            import torch
             from .. import _capi
+            copy = self.data.clone(memory_format=torch.contiguous_format)   # row-major whatever the caller's strides
             if isinstance(self.fill_value, Number):
-                return _capi.fill_unknown(self.data.clone(), FILL_CONST, self.fill_value)
-            return _capi.fill_unknown(self.data.clone(), self.fill_value)
+                return _capi.fill_unknown(copy, FILL_CONST, self.fill_value)
+            return _capi.fill_unknown(copy, self.fill_value)
         if isinstance(self.fill_value, Number):
             return FILL_TYPE[FILL_CONST](self.data, self.fill_value)
         return FILL_TYPE[self.fill_value](self.data)
