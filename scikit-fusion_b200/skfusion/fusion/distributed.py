@@ -13,8 +13,6 @@ The same loop drives any ``shard`` object with the five methods below: the CUDA 
 (``CudaShard``) in production, a numpy stand-in in the gloo CPU tests of the host logic.
 Transform and restarts do not shard: rows / runs are independent, so they run as replicas.
 """
-import numpy as np
-
 from .. import _capi
 
 
