@@ -39,48 +39,145 @@ def parse():
     # (not "--n": torch.distributed.run's own parser treats it as an ambiguous abbreviation of --nnodes / --nproc-per-node)
     ap.add_argument("--size", dest="n", type=int, default=0, help="objects per type (0 = 81920, shrunk if HBM is short)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--split-terms", type=int, default=2)
-    ap.add_argument("--cpu-n", type=int, default=4096, help="objects per type of the bounded CPU sample")
+    ap.add_argument("--split-terms", default="2", help="1..3, auto or centred1 (operand form of the factors, include/fz_fusion.h)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of host time the CPU arm may spend on its samples")
+    ap.add_argument("--cpu-sizes", default="4096,8192,16384", help="objects per type of the CPU arm's bounded samples")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="synthetic", choices=["synthetic", "readme3", "dicty", "transform"],
                     help="synthetic = the contract workload; readme3 / dicty = the small BASELINE configs C1 / C2 "
                          "(latency-bound; informational line, N=1 only); transform = config C5 (project 10 000 new "
                          "rows of type 0 against a 100 000-object model, 4 relations; informational line, N=1 only)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.cpu_sizes = tuple(int(x) for x in args.cpu_sizes.split(","))
+    if args.split_terms not in ("auto", "centred1"):
+        args.split_terms = int(args.split_terms)
+    return args
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(n_workload, n_sample, steps, warmup):
-    """Oracle (float64 numpy port of the reference, reference evaluation order, all host BLAS threads) on a
-    bounded sample of the workload: the same graph shape at n_sample and n_sample/2 objects per type.  The
-    iteration time is fitted as t(n) = a n^2 + b (three n x n x 64 GEMMs per relation + size-independent
-    k x k work) and evaluated at the workload size."""
+def _blas_threads():
+    """Give the BLAS pool every host core (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers) and report
+    the thread count the pool really runs with.  Returns (limiter to keep alive, threads, description)."""
+    from threadpoolctl import threadpool_info, threadpool_limits
+    want = os.cpu_count() or 1
+    limiter = threadpool_limits(limits=want)
+    blas = [lib for lib in threadpool_info() if lib.get("user_api") == "blas"]
+    used = max([int(lib.get("num_threads", 1)) for lib in blas] or [1])
+    desc = "; ".join("%s %s threads=%s" % (lib.get("internal_api"), lib.get("version"), lib.get("num_threads")) for lib in blas)
+    return limiter, used, "os.cpu_count()=%d, %s" % (want, desc or "no BLAS pool found")
+
+
+def _reference_dfmf():
+    """The reference's own dfmf() (skfusion/fusion/decomposition/_dfmf.py:127) from baseline/_ref (installed by
+    baseline/install_reference.sh, compat edits applied in memory), else the oracle port.  Returns (callable, kind)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_root, "skfusion", "fusion")) and os.environ.get("FZ_BENCH_CPU_PORT", "0") != "1":
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            import _load_reference as loader
+            loader.REF_ROOT = ref_root
+            ref_dfmf = loader.functions()[0]
+
+            def run(R, types, ranks, iters, callback):
+                return ref_dfmf(R, {}, types, ranks, max_iter=iters, init_type="random", random_state=np.random.RandomState(0),
+                                callback=callback, n_jobs=1)
+            return run, "reference"
+        except Exception as exc:     # an unusable install must not take the bench down: fall back to the port, say so
+            print("[bench] reference under baseline/_ref unusable (%r): timing the oracle port" % (exc,), file=sys.stderr)
     import fusion_oracle as oracle
 
-    def timed(n_s):
-        types, ranks, R = oracle.hashed_graph(n_s, N_TYPES, RANK, SEED0, "bfloat16")
-        stamps = []
-        oracle.dfmf(R, {}, types, ranks, max_iter=warmup + steps, init_type="random", random_state=np.random.RandomState(0),
-                    callback=lambda G, S, it: stamps.append(time.perf_counter()))
-        per_it = np.diff(stamps)[max(0, warmup - 1):]
-        return float(np.median(per_it)), len(per_it)
+    def run(R, types, ranks, iters, callback):
+        return oracle.dfmf(R, {}, types, ranks, max_iter=iters, init_type="random", random_state=np.random.RandomState(0),
+                           callback=callback)
+    return run, "port"
 
-    n_half = max(64, n_sample // 2)
-    if n_half >= n_sample:
-        n_half = max(1, n_sample // 2)
-    t_half, _ = timed(n_half)
-    t_full, count = timed(n_sample)
-    a = (t_full - t_half) / (float(n_sample) ** 2 - float(n_half) ** 2)
-    b = t_full - a * float(n_sample) ** 2
-    if a <= 0.0 or b < 0.0:        # noisy fit (tiny samples): fall back to pure n^2 scaling of the larger sample
-        a, b = t_full / float(n_sample) ** 2, 0.0
+
+def _cpu_graph(n_s):
+    """Benchmark-shaped graph for the CPU timing legs: bf16-representable uniform values as float64 (timing does not
+    depend on the values; the parity leg uses the engine's own counter-based generator instead)."""
+    rng = np.random.default_rng(SEED0)
+    types = list(range(N_TYPES))
+    R = {}
+    for (i, j) in PAIRS:
+        m = rng.random((n_s, n_s), dtype=np.float32)
+        m.view(np.uint32)[...] &= np.uint32(0xFFFF0000)
+        R[i, j] = [m.astype(np.float64)]
+    return types, {t: RANK for t in types}, R
+
+
+def cpu_arm(n_workload, budget_s=150.0, sizes=(4096, 8192, 16384), max_iters=5):
+    """The reference's dfmf (float64 numpy, n_jobs=1, all host BLAS threads) on bounded samples of the workload: the same
+    5-type / 10-relation graph at several sizes, per-iteration time from the callback hook (iteration 0 dropped, median),
+    least-squares fit t(n) = a n^2 + b (three n x n x 64 GEMMs per relation + size-independent k x k work), evaluated at
+    the workload size.  The largest directly measured point is reported next to it."""
+    import psutil
+    t_begin = time.perf_counter()
+    limiter, threads, thread_desc = _blas_threads()
+    run, kind = _reference_dfmf()
+    points = []
+    for n_s in sizes:
+        left = budget_s - (time.perf_counter() - t_begin)
+        est = points[-1]["s_per_it"] * (float(n_s) / points[-1]["n"]) ** 2 if points else 0.0
+        iters = max_iters
+        if points:
+            iters = int(min(max_iters, (left - 0.25 * est) // max(est, 1e-9)))     # 0.25 est: generating the inputs
+        need_b = 10.0 * n_s * n_s * 8 * 2.5
+        if points and (iters < 2 or need_b > psutil.virtual_memory().available):
+            break
+        types, ranks, R = _cpu_graph(n_s)
+        stamps = []
+        run(R, types, ranks, iters + 1, lambda G, S, it: stamps.append(time.perf_counter()))
+        per_it = np.diff(stamps)
+        points.append({"n": n_s, "s_per_it": float(np.median(per_it)), "timed_iterations": int(len(per_it))})
+        del R
+    ns = np.array([p["n"] for p in points], dtype=np.float64)
+    ts = np.array([p["s_per_it"] for p in points])
+    if len(points) >= 2:
+        A = np.stack([ns ** 2, np.ones_like(ns)], axis=1)
+        (a, b), *_ = np.linalg.lstsq(A, ts, rcond=None)
+        if a <= 0.0 or b < 0.0:
+            a, b = float(ts[-1] / ns[-1] ** 2), 0.0
+    else:
+        a, b = float(ts[-1] / ns[-1] ** 2), 0.0
+    resid = float(np.max(np.abs(a * ns ** 2 + b - ts) / ts))
     t_workload = a * float(n_workload) ** 2 + b
-    return {"t_sample_s": t_full, "value": 1.0 / t_workload, "cores": os.cpu_count(),
-            "sample": "oracle dfmf (float64 numpy port, reference evaluation order), same 5-type/10-relation graph at n=%d "
-                      "(%.3f s/it) and n=%d (%.3f s/it, median of %d timed iterations); t(n) = a n^2 + b fitted and "
-                      "evaluated at n=%d -> %.1f s/it" % (n_half, t_half, n_sample, t_full, count, n_workload, t_workload)}
+    del limiter
+    return {"value": 1.0 / t_workload, "cores": threads, "kind": kind, "points": points,
+            "fit": {"a_s_per_n2": float(a), "b_s": float(b), "max_rel_residual": round(resid, 4)},
+            "largest_measured": {"n": int(ns[-1]), "it_per_s": round(1.0 / float(ts[-1]), 5)},
+            "extrapolated": {"n": int(n_workload), "s_per_it": round(t_workload, 3)},
+            "threads": thread_desc,
+            "sample": "%s dfmf (float64 numpy, n_jobs=1, %d BLAS threads), same 5-type/10-relation rank-64 graph at %s: %s s/it "
+                      "(median, iteration 0 dropped); least-squares t(n) = a n^2 + b (max rel. residual %.1f%%) evaluated at n=%d "
+                      "-> %.1f s/it EXTRAPOLATED; largest measured point n=%d: %.4f it/s" % (
+                          "reference skfusion._dfmf" if kind == "reference" else "oracle port of", threads,
+                          ", ".join("n=%d" % p["n"] for p in points), ", ".join("%.3f" % p["s_per_it"] for p in points),
+                          100.0 * resid, n_workload, t_workload, int(ns[-1]), 1.0 / float(ts[-1]))}
+
+
+def parity_leg(split_terms, iters, n_s=2048):
+    """Driver-visible parity: the bench's own GPU code path (same generator, storage, operand form) on the same graph
+    shape at a size the float64 oracle finishes in seconds, compared factor by factor and backbone by backbone."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fusion_oracle as oracle
+    from skfusion.fusion import solver
+    types, ranks, R = oracle.hashed_graph(n_s, N_TYPES, RANK, SEED0, "bfloat16")
+    Go, So = oracle.dfmf(R, {}, types, ranks, max_iter=iters, init_type="random", random_state=np.random.RandomState(0))
+    G, S = solver.dfmf(R, {}, types, ranks, max_iter=iters, init_type="random", random_state=np.random.RandomState(0),
+                       dtype="float32", storage="bfloat16", split_terms=split_terms)
+    eg = max(float(np.linalg.norm(G[t, t] - Go[t, t]) / np.linalg.norm(Go[t, t])) for t in types)
+    es = max(float(np.linalg.norm(S[k][0] - So[k][0]) / np.linalg.norm(So[k][0])) for k in So)
+    return {"n_per_type": n_s, "iterations": iters, "relFro_G_max": eg, "relFro_S_max": es, "tolerance": {"G": 1e-3, "S": 5e-3},
+            "ok": bool(eg <= 1e-3 and es <= 5e-3), "oracle_check": _check_sums(Go, So, iters), "engine_check": _check_sums(G, S, iters)}
+
+
+def _check_sums(G, S, iters):
+    """One fp64 fingerprint of a fit: sum of the Frobenius norms of the factors and of the backbones."""
+    g = float(sum(np.linalg.norm(np.asarray(v, dtype=np.float64)) for v in G.values()))
+    sb = float(sum(np.linalg.norm(np.asarray(m, dtype=np.float64)) for v in S.values() for m in v))
+    return {"iterations": int(iters), "sum_fro_G": g, "sum_fro_S": sb}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -137,7 +234,7 @@ class ClockSampler(threading.Thread):
 
 
 def fused_kernel_active(args):
-    return os.environ.get("FZ_NO_FUSED", "0") != "1" and args.split_terms == 2
+    return os.environ.get("FZ_NO_FUSED", "0") != "1" and args.split_terms in (2, "auto", "centred1")
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -259,7 +356,7 @@ def gpu_arm(args):
         # relation element = 256 flop/B, above the measured ridge (sustained bf16 / HBM), and under random operands the
         # board sits at its power cap.  Reported next to the algorithmic (HBM) roofline, never instead of it.
         tf_peak = float(peaks.get("bf16_tflops_sustained", 0.0)) or None
-        executed = 2.0 * 128.0 * args.split_terms * (alg_bytes_per_launch / 2.0)      # flop per launch
+        executed = 2.0 * 128.0 * (1 if args.split_terms == 'centred1' else 2) * (alg_bytes_per_launch / 2.0)      # flop per launch
         tf = executed / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
         roofline["kernel"] = kernel_name + " (tcgen05/TMA, A and B from one stream of R)"
         roofline["tensor_executed"] = {"achieved": round(tf, 1), "peak": tf_peak, "unit": "TFLOP/s",
@@ -269,6 +366,11 @@ def gpu_arm(args):
 
     # ---- e2e: the same fit through the C ABI with HOST buffers (pinned), H2D of the relations and D2H of the
     # factors / backbones inside the timed region.
+    # ---- fingerprint of the state after exactly warmup + steps iterations: identical for every sharding of the graph
+    Gf = {(t, t): eng.get_factor(tid[t]) for t in types}
+    Sf = {key: [eng.get_backbone(i) for i in ids] for key, ids in rel_ids.items()}
+    check = _check_sums(Gf, Sf, args.warmup + args.steps)
+    del Gf, Sf
     e2e = None
     eng.close()                      # frees the engine's buffers and drops its references to the borrowed relations
     del shard
@@ -277,21 +379,23 @@ def gpu_arm(args):
 
     out = None
     if rank == 0:
-        cpu = None
+        cpu, parity = None, None
         if world == 1 and not args.no_cpu:
-            c = cpu_arm(n, args.cpu_n, 5, 1)
-            cpu = {"value": c["value"], "unit": "it/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
+            parity = parity_leg(args.split_terms, args.warmup + args.steps)
+            c = cpu_arm(n, budget_s=min(args.cpu_budget, 90.0), sizes=args.cpu_sizes)
+            cpu = {"value": c["value"], "unit": "it/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"],
+                   "points": c["points"], "fit": c["fit"], "largest_measured": c["largest_measured"], "threads": c["threads"]}
         out = {
             "metric": "DFMF iterations/sec on the synthetic 5-type 10-relation graph", "value": round(value, 4), "unit": "it/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "5 object types x n=%d objects, 10 relations (all pairs i<j) n x n stored bf16, rank 64, "
-                                   "init 'random', factors as %d-term bf16 split with fp32 accumulation, fp64 k x k chain; "
+                                   "init 'random', factor operand form split_terms=%s with fp32 accumulation, fp64 k x k chain; "
                                    "type rows sharded over %d GPU(s)" % (n, args.split_terms, world),
                        "n_per_type": n, "rank": RANK, "relations": len(PAIRS), "split_terms": args.split_terms,
                        "relation_bytes_total": 10 * n * n * 2,
                        "cache": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (10.0 * n * (hi - lo) * 2 / 1e9)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "check": check, "parity": parity,
             "clocks": sampler.summary(),
         }
     if world > 1:
@@ -528,17 +632,19 @@ def main():
         if rank != 0:
             return
         n = args.n if args.n > 0 else 81920
-        c = cpu_arm(n, args.cpu_n, args.steps, args.warmup)
+        c = cpu_arm(n, budget_s=args.cpu_budget, sizes=args.cpu_sizes, max_iters=max(2, min(5, args.steps)))
         print(json.dumps({
             "impl": "reference", "metric": "DFMF iterations/sec on the synthetic 5-type 10-relation graph",
             "value": c["value"], "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / c["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "5 object types x n=%d objects, 10 relations (all pairs i<j) n x n stored bf16, rank 64, "
-                                   "init 'random' -- the same graph as the GPU arm; CPU arm: float64 oracle port of the reference's "
-                                   "numpy path on all host cores, measured on a bounded sample and extrapolated (see cpu_baseline.sample)" % n,
+                                   "init 'random' -- the same graph as the GPU arm; CPU arm: the reference's float64 "
+                                   "numpy path on all host cores, measured on bounded samples and extrapolated (see cpu_baseline.sample)" % n,
                        "n_per_type": n, "rank": RANK, "relations": len(PAIRS), "relation_bytes_total": 10 * n * n * 2},
-            "cpu_baseline": {"value": c["value"], "unit": "it/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]},
+            "cpu_baseline": {"value": c["value"], "unit": "it/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"],
+                             "points": c["points"], "fit": c["fit"], "largest_measured": c["largest_measured"],
+                             "extrapolated": c["extrapolated"], "threads": c["threads"]},
             "e2e": {"value": c["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return

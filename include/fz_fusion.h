@@ -73,8 +73,19 @@ int fz_add_relation(fz_engine* e, int ti, int tj, const void* data, int64_t ld, 
 int fz_set_factor(fz_engine* e, int t, const void* G0, int64_t ld, int src, int mem);
 /* Frozen backbone S_ij for transform (k_ti x k_tj).  Reference: dfmf.py:112-114. */
 int fz_set_backbone(fz_engine* e, int rel, const void* S, int64_t ld, int src, int mem);
-/* number of bf16 split terms used for factors on the tensor-core path (1..3, default 2) */
+/* Operand form of the factors on the tensor-core path (bf16-stored relations):
+ *   1..3              plain form: G = G(0) + G(1) (+ G(2)), each term the bf16 rounding of the running residual (default 2)
+ *   FZ_TERMS_AUTO     mean-centred form G = 1 c^T + D (c = column means, exact rank-1 algebra outside the MMAs); per
+ *                     iteration the engine runs either the two-term kernel on D or the single-term kernel (half the tensor
+ *                     work and half the B flush per relation byte) with the first-order effect of the dropped residual
+ *                     restored in the fp64 backbone solve -- chosen from a measured estimate of the single-term error
+ *                     (DESIGN.md section 4); unsharded and sharded dfmf
+ *   FZ_TERMS_CENTRED1 always the single-term kernel (no accuracy gate: for studies) */
+enum { FZ_TERMS_AUTO = 0, FZ_TERMS_CENTRED1 = -1 };
 int fz_set_split_terms(fz_engine* e, int terms);
+/* dfmf iterations run so far with the single-term / the two-term fused kernel, and the last measured operand-form error and
+ * Gram condition estimate of the FZ_TERMS_AUTO gate (-1 before the first check).  Any pointer may be NULL. */
+int fz_operand_stats(fz_engine* e, int64_t* single_iters, int64_t* two_term_iters, double* err_estimate, double* cond_estimate);
 /* allocate workspaces, build TMA descriptors; must precede the calls below */
 int fz_finalize(fz_engine* e);
 

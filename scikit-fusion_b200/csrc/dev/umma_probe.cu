@@ -11,6 +11,8 @@
 #include "../umma_skinny.cuh"
 #include "../umma_fused.cuh"
 #include "../umma_fused_t.cuh"
+#include "../umma_fused1.cuh"
+#include "../fz_kernels.cuh"
 #include "../tmap.h"
 
 #define CK(x)                                                                          \
@@ -458,8 +460,162 @@ static int main_fused_t(int variant, int nbench) {
   return fails ? 1 : 0;
 }
 
+
+// ---- v5 (single-term, mean-centred operand form, 4 row blocks per CTA): A = X Gs_j + rowsum c_j^T, B = B0 + X^T Gs_i
+static int run_fused1_case(int rows, int cols, int ka, int kb, int csplit, int tma_flush = 1, int gi_row0 = 0, bool rank1 = true) {
+  const int N = 128;   // operand rows hold [hi | lo]; the kernel must read the hi half only
+  const int ld = (cols + 7) / 8 * 8;
+  const int gi_rows = gi_row0 + rows;
+  std::vector<__nv_bfloat16> hX((size_t)rows * ld), hGj((size_t)cols * N), hGi((size_t)gi_rows * N);
+  std::vector<float> fX((size_t)rows * ld), fGj((size_t)cols * 64, 0.f), fGi((size_t)gi_rows * 64, 0.f);
+  for (size_t i = 0; i < hX.size(); ++i) { hX[i] = __float2bfloat16(frand() - 0.3f); fX[i] = __bfloat162float(hX[i]); }
+  auto fillG = [&](std::vector<__nv_bfloat16>& h, std::vector<float>& f, int n, int k) {
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < N; ++c) {
+        const int q = c % 64;
+        float v = (q < k) ? (frand() - 0.5f) : 0.f;
+        if (c >= 64) v = 7.f;                                      // poison: the second term must be ignored
+        h[(size_t)r * N + c] = __float2bfloat16(v);
+        if (c < 64) f[(size_t)r * 64 + q] = __bfloat162float(h[(size_t)r * N + c]);
+      }
+  };
+  fillG(hGj, fGj, cols, ka);
+  fillG(hGi, fGi, gi_rows, kb);
+  std::vector<float> rowsum(rows, 0.f), colsum(cols, 0.f), cj(64, 0.f), ci(64, 0.f);
+  for (int r = 0; r < rows; ++r) { double s = 0; for (int c = 0; c < cols; ++c) s += fX[(size_t)r * ld + c]; rowsum[r] = (float)s; }
+  for (int c = 0; c < cols; ++c) { double s = 0; for (int r = 0; r < rows; ++r) s += fX[(size_t)r * ld + c]; colsum[c] = (float)s; }
+  for (int q = 0; q < 64; ++q) { cj[q] = q < ka ? 0.25f + 0.01f * q : 0.f; ci[q] = q < kb ? 0.5f - 0.005f * q : 0.f; }
+  __nv_bfloat16 *dX, *dGj, *dGi; float *dA, *dB, *dRs, *dCs, *dCj, *dCi;
+  CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dGj, hGj.size() * 2)); CK(cudaMalloc(&dGi, hGi.size() * 2));
+  CK(cudaMalloc(&dA, (size_t)rows * ka * 4)); CK(cudaMalloc(&dB, (size_t)cols * kb * 4));
+  CK(cudaMalloc(&dRs, rows * 4)); CK(cudaMalloc(&dCs, cols * 4)); CK(cudaMalloc(&dCj, 256)); CK(cudaMalloc(&dCi, 256));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dGj, hGj.data(), hGj.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dGi, hGi.data(), hGi.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dRs, rowsum.data(), rows * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dCs, colsum.data(), cols * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dCj, cj.data(), 256, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dCi, ci.data(), 256, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dA, 0, (size_t)rows * ka * 4));
+  if (rank1) rank1_init<<<(unsigned)(((size_t)cols * kb + 255) / 256), 256>>>(dB, kb, cols, cols, kb, dCs, dCi);
+  else CK(cudaMemset(dB, 0, (size_t)cols * kb * 4));
+  CUtensorMap tr, tgj, tgi, tb; std::string err;
+  if (kb % 4 != 0 || kb < 32) tma_flush = 0;
+  bool ok = make_tmap_bf16_2d(&tr, dX, rows, cols, ld, 64, 128, &err) && make_tmap_bf16_2d(&tgj, dGj, cols, N, N, 64, 128, &err) &&
+            make_tmap_bf16_2d(&tgi, dGi, gi_rows, N, N, 64, 128, &err);
+  if (ok && tma_flush) ok = make_tmap_f32_2d(&tb, dB, cols, kb, kb, 32, 32, &err);
+  if (!tma_flush) tb = tr;
+  if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
+  Fused1Params p;
+  p.A = dA; p.B = dB; p.lda = ka; p.ldb = kb; p.rowsum = rank1 ? dRs : nullptr; p.cj = dCj; p.n_rows = rows; p.n_cols = cols;
+  p.k_a = ka; p.k_b = kb; p.gi_row0 = gi_row0; p.probe = 0; p.tma_flush = tma_flush;
+  const int tiles = (cols + 127) / 128;
+  p.tiles_per_split = (tiles + csplit - 1) / csplit;
+  const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.a_atomic = splits > 1;
+  CK(cudaFuncSetAttribute(umma_fused1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF1SmemBytes));
+  dim3 grid((rows + kF1Blocks * 128 - 1) / (kF1Blocks * 128), splits);
+  umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tgj, tgi, tb, p);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hA((size_t)rows * ka), hB((size_t)cols * kb);
+  CK(cudaMemcpy(hA.data(), dA, hA.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hB.data(), dB, hB.size() * 4, cudaMemcpyDeviceToHost));
+  double ma = 0, ea = 0, mb = 0, eb = 0;
+  for (int m = 0; m < rows; ++m)
+    for (int q = 0; q < ka; ++q) {
+      double s = rank1 ? (double)rowsum[m] * cj[q] : 0.0;
+      for (int c = 0; c < cols; ++c) s += (double)fX[(size_t)m * ld + c] * (double)fGj[(size_t)c * 64 + q];
+      ma = fmax(ma, fabs(s)); ea = fmax(ea, fabs(s - hA[(size_t)m * ka + q]));
+    }
+  for (int c = 0; c < cols; ++c)
+    for (int q = 0; q < kb; ++q) {
+      double s = rank1 ? (double)colsum[c] * ci[q] : 0.0;
+      for (int r = 0; r < rows; ++r) s += (double)fX[(size_t)r * ld + c] * (double)fGi[(size_t)(gi_row0 + r) * 64 + q];
+      mb = fmax(mb, fabs(s)); eb = fmax(eb, fabs(s - hB[(size_t)c * kb + q]));
+    }
+  const bool good = ea / ma < 2e-5 && eb / mb < 2e-5;
+  printf("fused1 rows=%d cols=%d ka=%d kb=%d csplit=%d flush=%s gi_row0=%d rank1=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb,
+         splits, tma_flush ? "tma" : "red", gi_row0, (int)rank1, ea / ma, eb / mb, good ? "OK" : "FAIL");
+  cudaFree(dX); cudaFree(dGj); cudaFree(dGi); cudaFree(dA); cudaFree(dB); cudaFree(dRs); cudaFree(dCs); cudaFree(dCj); cudaFree(dCi);
+  return good ? 0 : 1;
+}
+
+static void bench_fused1(int n, int probe, int csplit = 1) {
+  const int N = 128, k = 64;
+  size_t elems = (size_t)n * n;
+  __nv_bfloat16 *dX, *dG; float *dA, *dB, *dRs, *dC;
+  CK(cudaMalloc(&dX, elems * 2)); CK(cudaMalloc(&dG, (size_t)n * N * 2));
+  CK(cudaMalloc(&dA, (size_t)n * k * 4)); CK(cudaMalloc(&dB, (size_t)n * k * 4)); CK(cudaMalloc(&dRs, (size_t)n * 4)); CK(cudaMalloc(&dC, 256));
+  CK(cudaMemset(dX, 0x3c, elems * 2)); CK(cudaMemset(dG, 0x3c, (size_t)n * N * 2)); CK(cudaMemset(dRs, 0, (size_t)n * 4)); CK(cudaMemset(dC, 0, 256));
+  if (g_sustain_s > 0) {   // random operands: switching activity (power) like real data; centred operands have both signs
+    fill_random_bf16<<<1184, 256>>>(dX, elems, 1u, 1.0f);
+    fill_random_bf16<<<1184, 256>>>(dG, (size_t)n * N, 2u, 1.0f);
+  }
+  CUtensorMap tr, tg, tb; std::string err;
+  bool ok = make_tmap_bf16_2d(&tr, dX, n, n, n, 64, 128, &err) && make_tmap_bf16_2d(&tg, dG, n, N, N, 64, 128, &err) &&
+            make_tmap_f32_2d(&tb, dB, n, k, k, 32, 32, &err);
+  if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
+  CK(cudaFuncSetAttribute(umma_fused1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF1SmemBytes));
+  Fused1Params p;
+  p.A = dA; p.B = dB; p.lda = k; p.ldb = k; p.rowsum = dRs; p.cj = dC; p.n_rows = n; p.n_cols = n; p.k_a = k; p.k_b = k; p.gi_row0 = 0;
+  p.probe = probe; p.tma_flush = 1;
+  const int tiles = (n + 127) / 128;
+  p.tiles_per_split = (tiles + csplit - 1) / csplit;
+  const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.a_atomic = splits > 1;
+  dim3 grid((n + kF1Blocks * 128 - 1) / (kF1Blocks * 128), splits);
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int w = 0; w < 2; ++w) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, p);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  int reps = 40;
+  float ms;
+  if (g_sustain_s > 0) {
+    reps = (int)(g_sustain_s * 0.5 / 0.6e-3);
+    for (int r = 0; r < reps; ++r) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, p);
+  }
+  CK(cudaEventRecord(e0));
+  for (int r = 0; r < reps; ++r) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, p);
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+  printf("bench FUSED1 probe=%d n=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s executed\n", probe, n, grid.x, grid.y,
+         ms, elems * 2.0 / 1e9 / (ms * 1e-3), 2.0 * 2.0 * elems * 64 / (ms * 1e-3) / 1e12);
+  cudaFree(dX); cudaFree(dG); cudaFree(dA); cudaFree(dB); cudaFree(dRs); cudaFree(dC);
+}
+
+static int main_fused1(int nbench, double sustain, int csplit) {
+  int fails = 0;
+  fails += run_fused1_case(128, 128, 64, 64, 1);
+  fails += run_fused1_case(512, 384, 64, 64, 1);
+  fails += run_fused1_case(640, 256, 64, 64, 1);                 // second CTA holds one row block only
+  fails += run_fused1_case(1000, 520, 64, 40, 1);
+  fails += run_fused1_case(520, 1000, 50, 64, 3);
+  fails += run_fused1_case(130, 77, 7, 12, 1);                    // red.global fallback, boxes larger than the tensors
+  fails += run_fused1_case(2048, 4096, 64, 64, 4);
+  fails += run_fused1_case(1000, 520, 64, 40, 1, 0);
+  fails += run_fused1_case(3000, 2100, 33, 36, 2);
+  fails += run_fused1_case(777, 3001, 64, 64, 1);
+  fails += run_fused1_case(777, 1001, 64, 64, 2, 1, 1024);        // sharded: factor rows offset
+  fails += run_fused1_case(500, 1001, 64, 48, 1, 1, 12500);
+  fails += run_fused1_case(1000, 520, 64, 40, 1, 1, 0, false);    // no rank-1 part
+  fails += run_fused1_case(4096, 8192, 64, 64, 8);
+  printf("fused1 correctness: %d failing cases\n", fails);
+  if (nbench > 0) {
+    g_sustain_s = 0;
+    for (int probe : {0, 1, 2, 4, 7}) bench_fused1(nbench, probe, csplit);   // full, no flush, no B MMA, no A MMA, TMA only
+    if (sustain > 0) {
+      g_sustain_s = sustain;
+      for (int probe : {0, 1, 2, 4, 7}) bench_fused1(nbench, probe, csplit);
+      bench_fused(nbench, 0);                                        // v3 for reference on the same box
+    }
+  }
+  return fails ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
   setvbuf(stdout, nullptr, _IONBF, 0);
+  if (argc > 1 && argv[1][0] == '1') return main_fused1(argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atof(argv[3]) : 0.0, argc > 4 ? atoi(argv[4]) : 2);
   if (argc > 1 && argv[1][0] == 'm') {   // single-term B-product (the fp16 variant of this probe hit an illegal instruction:
     int fails = 0;                       //  bf16 A x fp16 B is not a legal kind::f16 combination, profiles/r01b_mixed_format_probe.log)
     fails += run_fused_case(512, 384, 64, 64, 1, 1, 1);

@@ -63,6 +63,8 @@ struct PinvJob {
   double* P;               // k x k output
   double* work;            // 3 * k * k doubles
   int* info;               // [0] = 0 Cholesky, 1 Jacobi ; [1] = numerical rank
+  double* cond;            // [1] estimate of cond_2(gram): (max L_ii / min L_ii)^2 (Cholesky, a lower bound) or
+                           //     sigma_max / sigma_min over the kept singular values (Jacobi; 1e300 when rank-deficient)
   int k;
 };
 
@@ -119,6 +121,20 @@ pinv_spd(const PinvJob* __restrict__ jobs) {
     }
   }
   __syncthreads();
+  // A factorisation that went through says little about conditioning: pivots above 1e-10 max(diag) still allow
+  // singular values below scipy's cut-off (k eps sigma_max), which pinv would DROP rather than invert.  The diagonal of
+  // L bounds the condition number from below, cond_2 >= (max L_ii / min L_ii)^2: beyond 1 / (k eps) hand the matrix to
+  // the eigen-solve, which applies the cut-off rule exactly.
+  if (!s_fail) {
+    if (tid == 0) {
+      double lo = L[0], hi = L[0];
+      for (int i = 1; i < k; ++i) { lo = fmin(lo, L[(long long)i * k + i]); hi = fmax(hi, L[(long long)i * k + i]); }
+      const double c = (hi / lo) * (hi / lo);
+      if (job.cond) job.cond[0] = c;
+      if (c * (double)k * 2.220446049250313e-16 > 1.0) s_fail = 1;
+    }
+    __syncthreads();
+  }
   if (!s_fail) {
     // X = L^{-1} (lower triangular), one column per thread
     for (int j = tid; j < k; j += nth) {
@@ -215,9 +231,13 @@ pinv_spd(const PinvJob* __restrict__ jobs) {
     s_smax = sqrt(m);
     const double cut = (double)k * 2.220446049250313e-16 * s_smax;
     int rank = 0;
-    for (int p = 0; p < k; ++p) rank += (sqrt(X[p]) > cut);
+    double smin = s_smax;
+    for (int p = 0; p < k; ++p) {
+      if (sqrt(X[p]) > cut) { ++rank; smin = fmin(smin, sqrt(X[p])); }
+    }
     job.info[0] = 1;
     job.info[1] = rank;
+    if (job.cond) job.cond[0] = (rank == k && smin > 0.0) ? s_smax / smin : 1e300;
   }
   __syncthreads();
   const double cutoff = (double)k * 2.220446049250313e-16 * s_smax;

@@ -26,6 +26,7 @@
 #include "fz_kernels.cuh"
 #include "tmap.h"
 #include "umma_fused.cuh"
+#include "umma_fused1.cuh"
 #include "umma_fused_t.cuh"
 #include "umma_skinny.cuh"
 
@@ -149,6 +150,7 @@ class EngineBase {
   virtual void relation_norms(int rel, int axis, double* dst_host, cudaStream_t st) = 0;
   virtual void init_add_sampled_means(int t, int rel, const int32_t* idx_host, int p_c, cudaStream_t st) = 0;
   virtual void init_end() = 0;
+  virtual void operand_stats(int64_t* single_iters, int64_t* two_term_iters, double* err_estimate, double* cond_estimate) = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -248,6 +250,9 @@ class Engine : public EngineBase {
     DevBuf GsT;              // bf16 [128][ldt]: transposed operand form (umma_fused_t.cuh), fused kernel v4
     int64_t ldt = 0;
     CUtensorMap tmGT;        // box {64 cols, 128 rows}
+    DevBuf centre, centre_part;   // mean-centred operand form: column means of the factor (fp32 [64]) and their partial sums
+    int centre_chunks = 0;
+    long long centre_rows_per_chunk = 0;
     DevBuf gram_part;
     int gram_chunks = 0, gram_rows_per_chunk = 0;
     double* gram_raw = nullptr;  // inside `small`
@@ -275,13 +280,30 @@ class Engine : public EngineBase {
     bool has_backbone = false;
     CUtensorMap tmX, tmXT, tmEs, tmB;
     bool has_tmB = false;
+    DevBuf rowsum, colsum;       // centred operand form: row / column sums of the stored relation (fp32), computed once
+    bool sums_ready = false;
+    int corr_chunks = 0, corr_rows_per_chunk = 0;   // first-order correction of M (single-term form): extra slots of M_part
     CUtensorMap tmX256, tmB16;   // fused kernel v4: relation box {64 cols, 256 rows}; B box {64 cols, 64 rows}, no swizzle
     bool has_tmB16 = false, v4_ok = false;
   };
 
   int device_;
   int world_ = 1, rank_ = 0;
-  int terms_ = 2;
+  int terms_ = 2;           // split terms of the factor operand: 1..3 plain form; FZ_TERMS_AUTO / FZ_TERMS_CENTRED1: centred form
+  int gs_terms_ = 2;        // terms stored in Gs (the centred forms always keep [hi | lo])
+  bool centred_ = false;    // mean-centred operand form for the fused dfmf products (terms_ <= 0)
+  bool single_now_ = false; // this iteration's fused products use the single-term kernel (umma_fused1.cuh) + M correction
+  // ---- FZ_TERMS_AUTO: which kernel may run is decided from measurements (gate_measure / gate_decide)
+  int64_t it_count_ = 0;            // dfmf iterations run on this handle
+  bool gate_enabled_ = false;
+  bool gate_single_ = false;        // decision in force for the coming iterations
+  bool gate_check_now_ = false;     // the current iteration measures
+  double gate_e_ = -1.0, gate_cond_est_ = -1.0, gate_pred_ = -1.0;
+  int64_t n_single_ = 0, n_two_ = 0;
+  DevBuf gate_probe_;               // 2 x [128][64] fp32: slab products with the residual term
+  DevBuf gate_cond_;                // one double per type (pinv_spd)
+  double* gate_slots_ = nullptr;    // inside small_ (so they are summed over the ranks): per relation numA, denA, numB, denB
+  int64_t gate_slot_count_ = 0;
   int sm_count_ = 148;
   // auxiliary stream: the fp64 reductions (Gram, G_i^T A) run beside the streamed products and fill their tails
   cudaStream_t aux_ = nullptr;
@@ -422,7 +444,8 @@ class Engine : public EngineBase {
 
   void set_split_terms(int terms) override {
     if (finalized_) FZ_THROW(FZ_ERR_INVALID, "engine already finalized");
-    if (terms < 1 || terms > 3) FZ_THROW(FZ_ERR_INVALID, "split terms must be 1..3");
+    if (terms != FZ_TERMS_AUTO && terms != FZ_TERMS_CENTRED1 && (terms < 1 || terms > 3))
+      FZ_THROW(FZ_ERR_INVALID, "split terms must be 1..3, FZ_TERMS_AUTO or FZ_TERMS_CENTRED1");
     terms_ = terms;
   }
 
@@ -434,6 +457,10 @@ class Engine : public EngineBase {
     CUDA_OK(cudaGetDeviceProperties(&prop, device_));
     const int sms = prop.multiProcessorCount;
     sm_count_ = sms;
+    if (const char* nf = getenv("FZ_NO_FUSED")) fused_ = !(nf[0] == '1');
+    centred_ = (terms_ <= 0) && fused_ && kDT == FZ_F32;
+    if (terms_ <= 0 && !centred_) terms_ = 2;       // the centred forms exist for the fused fp32-engine products only
+    gs_terms_ = terms_ <= 0 ? 2 : terms_;
     if (const char* fv = getenv("FZ_FUSED_VER")) fused_ver_ = atoi(fv);
     if (fused_ver_ != 3 && fused_ver_ != 4) FZ_THROW(FZ_ERR_INVALID, "FZ_FUSED_VER must be 3 or 4");
     // fp64 all-reduce buffer: [gram_t ...][M_r ...]
@@ -441,7 +468,16 @@ class Engine : public EngineBase {
     for (auto& t : types_) small_count_ += (int64_t)t->k * t->k;
     for (auto& r : rels_)
       if (!r->theta) small_count_ += (int64_t)types_[r->ti]->k * types_[r->tj]->k;
+    int64_t gate_off = small_count_;
+    if (centred_ && terms_ == FZ_TERMS_AUTO) {
+      for (auto& r : rels_)
+        if (!r->theta && r->storage == FZ_BF16) gate_slot_count_ += 4;
+      small_count_ += gate_slot_count_;
+      gate_probe_.alloc((size_t)2 * 128 * 64 * sizeof(float));
+    }
+    gate_cond_.alloc(types_.size() * 8);
     small_.alloc((size_t)small_count_ * 8);
+    gate_slots_ = small_.template as<double>() + gate_off;
     int64_t off = 0;
     for (auto& tp : types_) {
       TypeRec& t = *tp;
@@ -461,7 +497,13 @@ class Engine : public EngineBase {
         t.thP.alloc((size_t)t.m_loc * t.k * sizeof(T));
         t.thN.alloc((size_t)t.m_loc * t.k * sizeof(T));
       }
-      if (t.need_gs && fused_ver_ == 4 && terms_ == 2 && kDT == FZ_F32) {
+      if (t.need_gs && centred_) {
+        t.centre.alloc(64 * sizeof(float));
+        t.centre_rows_per_chunk = std::max<long long>(256, (t.n + 4 * sms - 1) / (4 * sms));
+        t.centre_chunks = (int)std::max<long long>(1, (t.n + t.centre_rows_per_chunk - 1) / t.centre_rows_per_chunk);
+        t.centre_part.alloc((size_t)t.centre_chunks * t.k * 8);
+      }
+      if (t.need_gs && fused_ver_ == 4 && gs_terms_ == 2 && kDT == FZ_F32) {
         t.ldt = ((t.n_pad + 255) / 256) * 256 + 256;   // a CTA preloads 256 rows from any local row offset
         t.GsT.alloc((size_t)128 * t.ldt * 2);
         CUDA_OK(cudaMemset(t.GsT.p, 0, t.GsT.bytes));
@@ -470,10 +512,10 @@ class Engine : public EngineBase {
           FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
       }
       if (t.need_gs) {
-        t.Gs.alloc((size_t)t.n_pad * terms_ * kKp * 2);
+        t.Gs.alloc((size_t)t.n_pad * gs_terms_ * kKp * 2);
         std::string e;
-        if (!make_tmap_bf16_2d(&t.tmG, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 64, &e) ||
-            !make_tmap_bf16_2d(&t.tmG128, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 128, &e))
+        if (!make_tmap_bf16_2d(&t.tmG, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 64, &e) ||
+            !make_tmap_bf16_2d(&t.tmG128, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 128, &e))
           FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
       }
     }
@@ -489,7 +531,14 @@ class Engine : public EngineBase {
       if (world_ > 1) r.Bloc.alloc((size_t)Tj.m_loc * Ti.k * sizeof(T));
       r.m_rows_per_chunk = Ti.gram_rows_per_chunk;
       r.m_chunks = Ti.gram_chunks;
-      r.M_part.alloc((size_t)r.m_chunks * Ti.k * Tj.k * 8);
+      if (centred_ && r.storage == FZ_BF16) {
+        r.corr_rows_per_chunk = (int)std::max<int64_t>(64, (Tj.n_pad + 2 * sms - 1) / (2 * sms));
+        r.corr_rows_per_chunk = ((r.corr_rows_per_chunk + 15) / 16) * 16;
+        r.corr_chunks = (int)std::max<int64_t>(1, (Tj.n_pad + r.corr_rows_per_chunk - 1) / r.corr_rows_per_chunk);
+        r.rowsum.alloc((size_t)std::max<int64_t>(1, r.rows_loc) * sizeof(float));
+        r.colsum.alloc((size_t)r.cols * sizeof(float));
+      }
+      r.M_part.alloc((size_t)(r.m_chunks + r.corr_chunks) * Ti.k * Tj.k * 8);
       r.S.alloc((size_t)Ti.k * Tj.k * 8);
       r.t2.alloc((size_t)Ti.k * Ti.k * 8);
       r.t5.alloc((size_t)Tj.k * Tj.k * 8);
@@ -516,9 +565,8 @@ class Engine : public EngineBase {
       }
     }
     err_acc_.alloc(8);
-    if (const char* nf = getenv("FZ_NO_FUSED")) fused_ = !(nf[0] == '1');
     if (const char* cs = getenv("FZ_FUSED_CSPLIT")) fused_csplit_ = atoi(cs);
-    if (terms_ != 2) fused_ = false;
+    if (gs_terms_ != 2) fused_ = false;
     if (const char* na = getenv("FZ_NO_AUX")) use_aux_ = !(na[0] == '1');
     if (const char* ng = getenv("FZ_NO_GRAPH")) use_graph_ = !(ng[0] == '1');
     if (use_graph_) {
@@ -533,6 +581,7 @@ class Engine : public EngineBase {
       ev_rel_.resize(rels_.size());
       for (auto& e : ev_rel_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    gate_enabled_ = centred_ && terms_ == FZ_TERMS_AUTO && !graph_worthwhile();   // small graphs are launch-bound: nothing to gain
     build_job_tables();
     // opt in to the large dynamic shared memory of the tensor-core kernels
     set_umma_attrs();
@@ -628,9 +677,12 @@ class Engine : public EngineBase {
     need_final();
     check_factors();
     if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_UNSUPPORTED, "piecewise products are for dfmf");
-    if (!use_aux_) { grams(st); return; }
+    single_now_ = centred_ && choose_single();
+    gate_check_now_ = gate_enabled_ && (it_count_ < 4 || (it_count_ % 8) == 0);
+    if (gate_slot_count_ > 0) CUDA_OK(cudaMemsetAsync(gate_slots_, 0, (size_t)gate_slot_count_ * 8, st));
+    if (!use_aux_) { grams(st, centred_); return; }
     for (auto& tp : types_)
-      if (tp->need_gs) split(*tp, st);                 // operand forms first: every streamed product needs them
+      if (tp->need_gs) split(*tp, st, centred_);       // operand forms first: every streamed product needs them
     CUDA_OK(cudaEventRecord(ev_fork_, st));
     CUDA_OK(cudaStreamWaitEvent(aux_, ev_fork_, 0));
     for (auto& tp : types_) gram_of(*tp, aux_);        // Gram matrices beside the first streamed products
@@ -643,10 +695,11 @@ class Engine : public EngineBase {
       product_A(r, st);
       product_B(r, st);
     }
-    if (!use_aux_) { reduce_M(r, st); return; }
+    if (!use_aux_) { reduce_M(r, st); if (gate_check_now_) gate_measure(r, rel, st); return; }
     CUDA_OK(cudaEventRecord(ev_rel_[rel], st));        // A_ij is complete here
     CUDA_OK(cudaStreamWaitEvent(aux_, ev_rel_[rel], 0));
     reduce_M(r, aux_);                                 // G_i^T A_ij overlaps the next relation's stream
+    if (gate_check_now_) gate_measure(r, rel, aux_);
   }
   void phase_products_end(int algo, cudaStream_t st) override {
     (void)algo;
@@ -662,6 +715,12 @@ class Engine : public EngineBase {
     need_final();
     const bool dfmf = (algo == FZ_DFMF);
     run_chain(/*solve=*/true, /*scrub=*/dfmf, st);
+    if (dfmf) {
+      if (single_now_) ++n_single_; else ++n_two_;
+      if (gate_check_now_) gate_decide(st);
+      gate_check_now_ = false;
+      ++it_count_;
+    }
     if (!dfmf) {
       for (auto& rp : rels_) {                                   // _dfmc.py:319-325
         RelRec& r = *rp;
@@ -741,12 +800,12 @@ class Engine : public EngineBase {
       gemm(cur(To), To.k, W, Tt.k, r.E.template as<T>(), Tt.k, (int)To.n, Tt.k, To.k, false, st);
       r.Cx.alloc((size_t)Tt.n * Tt.k * sizeof(T));
       if (r.storage == FZ_BF16) {
-        r.Es.alloc((size_t)To.n * terms_ * kKp * 2);
+        r.Es.alloc((size_t)To.n * gs_terms_ * kKp * 2);
         split_factor<T><<<nblk(To.n * kKp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(),
-                                                                To.n, To.n, Tt.k, kKp, terms_);
+                                                                To.n, To.n, Tt.k, kKp, gs_terms_);
         ++launches;
         std::string e;
-        if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 64, &e))
+        if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 64, &e))
           FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
         umma(r, /*trans=*/!row_role, r.tmEs, 0, r.Cx.template as<T>(), Tt.k, (int)Tt.n, (int)To.n, Tt.k, st);
       } else {
@@ -908,12 +967,12 @@ class Engine : public EngineBase {
     }
     r.Cx.alloc((size_t)Tt.n * Tt.k * sizeof(T));
     if (r.storage == FZ_BF16) {
-      r.Es.alloc((size_t)To.n * terms_ * kKp * 2);
+      r.Es.alloc((size_t)To.n * gs_terms_ * kKp * 2);
       split_factor<T><<<nblk(To.n * kKp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(), To.n, To.n,
-                                                              Tt.k, kKp, terms_);
+                                                              Tt.k, kKp, gs_terms_);
       ++launches;
       std::string e;
-      if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n, (uint64_t)terms_ * kKp, (uint64_t)terms_ * kKp, 64, 64, &e))
+      if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 64, &e))
         FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
       umma(r, /*trans=*/!row_role, r.tmEs, 0, r.Cx.template as<T>(), Tt.k, (int)Tt.n, (int)To.n, Tt.k, st);
     } else {
@@ -923,6 +982,12 @@ class Engine : public EngineBase {
     add_abs_mean<T><<<nblk(Tt.n * Tt.k, 256), 256, 0, st>>>(r.Cx.template as<T>(), cur(Tt), Tt.n * Tt.k, (T)p_c);
     ++launches;
     CUDA_OK(cudaGetLastError());
+  }
+  void operand_stats(int64_t* single_iters, int64_t* two_term_iters, double* err_estimate, double* cond_estimate) override {
+    if (single_iters) *single_iters = n_single_;
+    if (two_term_iters) *two_term_iters = n_two_;
+    if (err_estimate) *err_estimate = gate_e_;
+    if (cond_estimate) *cond_estimate = gate_cond_est_;
   }
   void init_end() override {
     need_final();
@@ -982,6 +1047,7 @@ class Engine : public EngineBase {
     umma_attr<128, false>(); umma_attr<128, true>();
     umma_attr<192, false>(); umma_attr<192, true>();
     cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes);
+    cudaFuncSetAttribute(umma_fused1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF1SmemBytes);
     cudaFuncSetAttribute(umma_fused_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes);
     cudaFuncSetAttribute(pinv_spd, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
     cudaFuncSetAttribute(backbone_chain<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
@@ -989,9 +1055,16 @@ class Engine : public EngineBase {
   // tensor-core product of a bf16 relation with a split factor:  C (M x k) = op(R) * Gs[g_row0 + ., :]
   void umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g_row0, T* C, int64_t ldc, int M, int K, int k, cudaStream_t st);
 
-  void split(TypeRec& t, cudaStream_t st) {
+  void split(TypeRec& t, cudaStream_t st, bool centred = false) {
+    const float* centre = nullptr;
+    if (centred) {     // G = 1 c^T + D with c the column means; the bf16 terms represent D
+      col_sum_partial<T><<<t.centre_chunks, 256, 0, st>>>(cur(t), t.k, t.n, t.k, t.centre_rows_per_chunk, t.centre_part.template as<double>());
+      finish_centre<<<1, 64, 0, st>>>(t.centre_part.template as<double>(), t.centre_chunks, t.k, t.n, t.centre.template as<float>());
+      launches += 2;
+      centre = t.centre.template as<float>();
+    }
     split_factor<T><<<nblk(t.n_pad * kKp, 256), 256, 0, st>>>(cur(t), t.k, t.Gs.template as<__nv_bfloat16>(), t.n, t.n_pad, t.k, kKp,
-                                                               terms_);
+                                                               gs_terms_, centre);
     ++launches;
     if (t.GsT.p != nullptr) {
       split_factor_t<T><<<nblk(t.n_pad, 64), 256, 0, st>>>(cur(t), t.k, t.GsT.template as<__nv_bfloat16>(), t.ldt, t.n, t.ldt, t.k);
@@ -1009,9 +1082,9 @@ class Engine : public EngineBase {
                                                                      (long long)t.k * t.k);
     launches += 2;
   }
-  void grams(cudaStream_t st) {
+  void grams(cudaStream_t st, bool centred = false) {
     for (auto& tp : types_) {
-      if (tp->need_gs) split(*tp, st);
+      if (tp->need_gs) split(*tp, st, centred);
       gram_of(*tp, st);
     }
   }
@@ -1041,9 +1114,68 @@ class Engine : public EngineBase {
     dim3 g(r.m_chunks, nblk(Ti.k, 64), nblk(Tj.k, 64));
     gram_partial<T><<<g, 256, 0, st>>>(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.A.template as<T>(), Tj.k, r.M_part.template as<double>(),
                                        r.rows_loc, Ti.k, Tj.k, r.m_rows_per_chunk, 0);
-    reduce_partials<<<nblk((long long)Ti.k * Tj.k, 32), 256, 0, st>>>(r.M_part.template as<double>(), r.M_raw, r.m_chunks,
+    int chunks = r.m_chunks;
+    if (single_now_ && r.storage == FZ_BF16) { corr_M(r, st); chunks += r.corr_chunks; }
+    reduce_partials<<<nblk((long long)Ti.k * Tj.k, 32), 256, 0, st>>>(r.M_part.template as<double>(), r.M_raw, chunks,
                                                                        (long long)Ti.k * Tj.k);
     launches += 2;
+  }
+  // Single-term operand form: G_i^T R G_j = G_i^T (R Gs_j + rowsum c_j^T) + (R^T G_i)^T lo_j, and R^T G_i is B up to second
+  // order in the residuals.  The partials land behind the M partials and are summed with them in fp64.
+  void corr_M(RelRec& r, cudaStream_t st);
+  // Which fused kernel runs this iteration's products (centred operand form only)
+  bool choose_single() {
+    if (terms_ == FZ_TERMS_CENTRED1) return true;
+    if (const char* fs = getenv("FZ_FORCE_SINGLE")) return fs[0] == '1';
+    return gate_enabled_ && gate_single_;
+  }
+  // The single-term form drops R lo_j from A and R^T lo_i from B (lo = the residual bf16 term).  Measure exactly that on a
+  // slab of the relation -- its first 128 rows for A, its first 128 columns for B -- with the tensor cores themselves:
+  // slots += { |R_slab lo_j|^2, |A_slab|^2, |R_slab^T lo_i|^2, |B_slab|^2 }.  The slots sit in the all-reduce buffer, so a
+  // sharded run decides from the sums over the ranks and every rank decides alike.
+  void gate_measure(RelRec& r, int rel, cudaStream_t st);
+  // Predicted factor error of the single-term form = e (8 + 0.2 sqrt(cond)), e the largest measured relative operand-form
+  // error, cond the largest Gram condition estimate: calibrated against the float64 oracle on the synthetic graphs of every
+  // initialisation and on dicty (scripts/precision_study.py); single-term runs while it stays below
+  // half the stated factor tolerance (1e-3).  One small D2H copy + stream sync per check.
+  void gate_decide(cudaStream_t st) {
+    std::vector<double> slots((size_t)gate_slot_count_), conds(types_.size());
+    if (gate_slot_count_ > 0) CUDA_OK(cudaMemcpyAsync(slots.data(), gate_slots_, slots.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(conds.data(), gate_cond_.p, conds.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    double e = 0.0, cond = 1.0;
+    for (size_t i = 0; i + 1 < slots.size(); i += 2) {
+      const double num = slots[i], den = slots[i + 1];
+      if (den > 0.0) e = std::max(e, std::sqrt(num / den));
+      else if (num > 0.0) e = 1.0;
+    }
+    for (double c : conds) cond = std::max(cond, (c == c) ? c : 1e300);
+    gate_e_ = e;
+    gate_cond_est_ = cond;
+    gate_pred_ = e * (8.0 + 0.2 * std::sqrt(cond));
+    gate_single_ = gate_pred_ <= 5e-4;
+    if (const char* gl = getenv("FZ_GATE_LOG"))
+      if (gl[0] == '1')
+        fprintf(stderr, "[fz gate] iteration %lld: operand-form error %.3g, cond %.3g, predicted %.3g -> %s\n", (long long)it_count_, e,
+                cond, gate_pred_, gate_single_ ? "single-term" : "two-term");
+  }
+  // row / column sums of a stored bf16 relation (the relation never changes during dfmf): once per handle
+  void ensure_sums(RelRec& r, cudaStream_t st) {
+    if (r.sums_ready) return;
+    if (r.rows_loc > 0) {
+      row_sums<__nv_bfloat16><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, r.rowsum.template as<float>());
+      const int chunks = (int)std::min<int64_t>(128, std::max<int64_t>(1, (r.rows_loc + 127) / 128));
+      const int64_t rpc = (r.rows_loc + chunks - 1) / chunks;
+      DevBuf part;
+      part.alloc((size_t)chunks * r.cols * 8, false);
+      dim3 g(nblk(r.cols, 256), chunks);
+      col_sums_partial<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, rpc, part.template as<double>());
+      finish_col_sums<<<nblk(r.cols, 256), 256, 0, st>>>(part.template as<double>(), r.colsum.template as<float>(), chunks, r.cols);
+      launches += 3;
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaStreamSynchronize(st));   // the partial buffer dies here (once per relation and handle)
+    }
+    r.sums_ready = true;
   }
   void theta_products(cudaStream_t st) {         // Theta+ G -> den, Theta- G -> num   (_dfmf.py:284-292)
     for (auto& tp : types_) {
@@ -1071,6 +1203,7 @@ class Engine : public EngineBase {
       j.P = t.P.template as<double>();
       j.work = t.pinv_work.template as<double>();
       j.info = t.info.template as<int>();
+      j.cond = gate_cond_.template as<double>() + pj.size();
       j.k = t.k;
       pj.push_back(j);
     }
@@ -1235,7 +1368,7 @@ void Engine<float>::umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g
   p.K = K;
   p.k = k;
   p.kp = kKp;
-  p.terms = terms_;
+  p.terms = gs_terms_;
   p.g_row0 = (int)g_row0;
   // split the reduction so that the grid covers the machine a few times over
   const int row_blocks = (M + kSkBM - 1) / kSkBM;
@@ -1249,7 +1382,7 @@ void Engine<float>::umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g
   p.atomic = ksplit > 1 ? 1 : 0;
   if (p.atomic) CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st));
   const CUtensorMap& tx = trans ? r.tmXT : r.tmX;
-  const int N = terms_ * kKp;
+  const int N = gs_terms_ * kKp;
   prof_begin(st);
   if (N == 64) { if (trans) umma_launch<64, true>(tx, tg, p, ksplit, st); else umma_launch<64, false>(tx, tg, p, ksplit, st); }
   else if (N == 128) { if (trans) umma_launch<128, true>(tx, tg, p, ksplit, st); else umma_launch<128, false>(tx, tg, p, ksplit, st); }
@@ -1274,7 +1407,13 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   p.probe_skip_flush = 0;
   p.b_terms = 2;
   p.tma_flush = r.has_tmB ? 1 : 0;
-  const int pairs = (int)((r.rows_loc + 2 * kFuTile - 1) / (2 * kFuTile));
+  if (centred_) {
+    ensure_sums(r, st);
+    p.rowsum = r.rowsum.template as<float>();
+    p.cj = Tj.centre.template as<float>();
+  }
+  const int rows_per_cta = single_now_ ? kF1Blocks * kF1Tile : 2 * kFuTile;
+  const int pairs = (int)((r.rows_loc + rows_per_cta - 1) / rows_per_cta);
   const int tiles = (int)((r.cols + kFuTile - 1) / kFuTile);
   int splits = fused_csplit_;
   if (splits <= 0) {
@@ -1297,11 +1436,23 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   p.tiles_per_split = (tiles + splits - 1) / splits;
   splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.a_atomic = splits > 1 ? 1 : 0;
-  CUDA_OK(cudaMemsetAsync(r.B.p, 0, r.B.bytes, st));
+  if (centred_) {    // B starts from the rank-1 part colsum(R) c_i^T of the centred form
+    rank1_init<<<nblk(Tj.n_pad * Ti.k, 256), 256, 0, st>>>(r.B.template as<float>(), Ti.k, Tj.n_pad, r.cols, Ti.k, r.colsum.template as<float>(),
+                                                           Ti.centre.template as<float>());
+    ++launches;
+  } else {
+    CUDA_OK(cudaMemsetAsync(r.B.p, 0, r.B.bytes, st));
+  }
   if (p.a_atomic) CUDA_OK(cudaMemsetAsync(r.A.p, 0, (size_t)r.rows_loc * Tj.k * sizeof(float), st));
   dim3 grid(pairs, splits);
   prof_begin(st);
-  if (fused_ver_ == 4 && r.v4_ok) {
+  if (single_now_) {
+    Fused1Params q;
+    q.A = p.A; q.B = p.B; q.lda = p.lda; q.ldb = p.ldb; q.rowsum = p.rowsum; q.cj = p.cj;
+    q.n_rows = p.n_rows; q.n_cols = p.n_cols; q.k_a = p.k_a; q.k_b = p.k_b; q.gi_row0 = p.gi_row0;
+    q.tiles_per_split = p.tiles_per_split; q.a_atomic = p.a_atomic; q.tma_flush = p.tma_flush; q.probe = 0;
+    umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes, st>>>(r.tmX, Tj.tmG128, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX, q);
+  } else if (fused_ver_ == 4 && r.v4_ok && !centred_) {
     FusedTParams q;
     q.A = p.A; q.B = p.B; q.lda = p.lda; q.ldb = p.ldb;
     q.GiT = Ti.GsT.template as<__nv_bfloat16>();
@@ -1320,6 +1471,56 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
 }
 template <>
 bool Engine<double>::product_AB_fused(RelRec&, cudaStream_t) { return false; }
+template <>
+void Engine<float>::corr_M(RelRec& r, cudaStream_t st) {
+  TypeRec& Ti = *types_[r.ti];
+  TypeRec& Tj = *types_[r.tj];
+  dim3 g(r.corr_chunks, nblk(Ti.k, 64), nblk(Tj.k, 64));
+  corr_partial<<<g, 256, 0, st>>>(r.B.template as<float>(), Ti.k, cur(Tj), Tj.k, Tj.Gs.template as<__nv_bfloat16>(), (long long)gs_terms_ * kKp,
+                                  Tj.centre.template as<float>(), r.M_part.template as<double>() + (size_t)r.m_chunks * Ti.k * Tj.k,
+                                  Tj.n, Ti.k, Tj.k, r.corr_rows_per_chunk);
+  ++launches;
+}
+template <>
+void Engine<double>::corr_M(RelRec&, cudaStream_t) {}
+template <>
+void Engine<float>::gate_measure(RelRec& r, int rel, cudaStream_t st) {
+  if (r.theta || r.storage != FZ_BF16 || r.rows_loc <= 0) return;
+  TypeRec& Ti = *types_[r.ti];
+  TypeRec& Tj = *types_[r.tj];
+  int slot = 0;
+  for (int q = 0; q < rel; ++q)
+    if (!rels_[q]->theta && rels_[q]->storage == FZ_BF16) slot += 4;
+  float* probe_a = gate_probe_.template as<float>();
+  float* probe_b = probe_a + 128 * 64;
+  CUDA_OK(cudaMemsetAsync(probe_a, 0, (size_t)2 * 128 * 64 * sizeof(float), st));
+  for (int side = 0; side < 2; ++side) {
+    const bool trans = side == 1;
+    SkinnyParams p;
+    p.C = trans ? probe_b : probe_a;
+    p.ldc = 64;
+    p.M = (int)std::min<int64_t>(128, trans ? r.cols : r.rows_loc);
+    p.K = (int)(trans ? r.rows_loc : r.cols);
+    p.k = trans ? Ti.k : Tj.k;
+    p.kp = kKp;
+    p.terms = 1;
+    p.g_row0 = trans ? (int)Ti.row0 : 0;
+    p.g_col0 = kKp;                                   // the residual term
+    int ksplit = std::max(1, std::min(sm_count_, (p.K + 1023) / 1024));
+    const int kps = ((p.K + ksplit - 1) / ksplit + 63) / 64 * 64;
+    ksplit = (p.K + kps - 1) / kps;
+    p.k_per_split = kps;
+    p.atomic = 1;
+    dim3 grid(1, ksplit);
+    if (trans) umma_skinny_kernel<64, true><<<grid, kSkThreads, SkinnyCfg<64>::kSmemBytes, st>>>(r.tmXT, Ti.tmG, p);
+    else umma_skinny_kernel<64, false><<<grid, kSkThreads, SkinnyCfg<64>::kSmemBytes, st>>>(r.tmX, Tj.tmG, p);
+    slab_sumsq<<<1, 256, 0, st>>>(p.C, 64, trans ? r.B.template as<float>() : r.A.template as<float>(), trans ? Ti.k : Tj.k, p.M, p.k,
+                                  gate_slots_ + slot + 2 * side);
+    launches += 2;
+  }
+}
+template <>
+void Engine<double>::gate_measure(RelRec&, int, cudaStream_t) {}
 
 template <>
 void Engine<double>::umma(RelRec&, bool, const CUtensorMap&, int64_t, double*, int64_t, int, int, int, cudaStream_t) {
@@ -1515,6 +1716,9 @@ int fz_init_add_sampled_means(fz_engine* e, int t, int rel, const int32_t* idx_h
 }
 int fz_init_end(fz_engine* e) {
   FZ_GUARD(e, e->impl->init_end())
+}
+int fz_operand_stats(fz_engine* e, int64_t* single_iters, int64_t* two_term_iters, double* err_estimate, double* cond_estimate) {
+  FZ_GUARD(e, e->impl->operand_stats(single_iters, two_term_iters, err_estimate, cond_estimate))
 }
 
 int fz_profile(fz_engine* e, int enable) {

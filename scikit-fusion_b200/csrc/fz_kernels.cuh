@@ -532,18 +532,167 @@ __global__ void row_norms(const XT* __restrict__ X, long long ld, long long rows
 // ------------------------------------------------------------------------------------------------
 template <class T>
 __global__ void split_factor(const T* __restrict__ G, long long ldg, __nv_bfloat16* __restrict__ Gs, long long n_valid,
-                             long long n_pad, int k, int kp, int terms) {
+                             long long n_pad, int k, int kp, int terms, const float* __restrict__ centre = nullptr) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_pad * kp) return;
   const long long r = idx / kp;
   const int q = (int)(idx % kp);
   float v = 0.f;
-  if (r < n_valid && q < k) v = (float)G[r * ldg + q];
+  if (r < n_valid && q < k) {
+    v = (float)G[r * ldg + q];
+    if (centre != nullptr) v -= centre[q];      // mean-centred operand form: G = 1 c^T + D, the terms represent D
+  }
   __nv_bfloat16* out = Gs + r * (long long)(kp * terms) + q;
   for (int t = 0; t < terms; ++t) {
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     out[(long long)t * kp] = h;
     v -= __bfloat162float(h);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mean-centred single-term operand form (umma_fused1.cuh): centre of a factor, rank-1 parts, first-order correction.
+// ------------------------------------------------------------------------------------------------
+// part[chunk][q] = sum of G[r][q] over the chunk's rows (fp64); grid = chunks, 256 threads (4 row lanes x 64 columns)
+template <class T>
+__global__ void __launch_bounds__(256)
+col_sum_partial(const T* __restrict__ G, long long ldg, long long n, int k, long long rows_per_chunk, double* __restrict__ part) {
+  __shared__ double red[4][64];
+  const int q = threadIdx.x & 63, lane = threadIdx.x >> 6;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = r0 + rows_per_chunk < n ? r0 + rows_per_chunk : n;
+  double s = 0.0;
+  if (q < k)
+    for (long long r = r0 + lane; r < r1; r += 4) s += (double)G[r * ldg + q];
+  red[lane][q] = s;
+  __syncthreads();
+  if (lane == 0 && q < k) part[(long long)blockIdx.x * k + q] = red[0][q] + red[1][q] + red[2][q] + red[3][q];
+}
+// centre[q] = (sum_chunks part[chunk][q]) / n   (fixed order); one block of 64 threads
+__global__ void finish_centre(const double* __restrict__ part, int chunks, int k, long long n, float* __restrict__ centre) {
+  const int q = threadIdx.x;
+  if (q >= 64) return;
+  double s = 0.0;
+  if (q < k)
+    for (int c = 0; c < chunks; ++c) s += part[(long long)c * k + q];
+  centre[q] = (q < k && n > 0) ? (float)(s / (double)n) : 0.f;
+}
+// row sums (one warp per row) and partial column sums of a stored relation, fp64 accumulation -> fp32
+template <class XT>
+__global__ void row_sums(const XT* __restrict__ X, long long ld, long long rows, long long cols, float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (long long c = lane; c < cols; c += 32) s += load_as<XT, double>(X + r * ld + c);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = (float)s;
+}
+template <class XT>
+__global__ void col_sums_partial(const XT* __restrict__ X, long long ld, long long rows, long long cols, long long rows_per_chunk,
+                                 double* __restrict__ part) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  double s = 0.0;
+  for (long long r = r0; r < r1; ++r) s += load_as<XT, double>(X + r * ld + c);
+  part[(long long)blockIdx.y * cols + c] = s;
+}
+__global__ void finish_col_sums(const double* __restrict__ part, float* __restrict__ out, int chunks, long long cols) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double s = 0.0;
+  for (int k = 0; k < chunks; ++k) s += part[(long long)k * cols + c];
+  out[c] = (float)s;
+}
+// out[0] = sum of squares of X (rows x k, leading dimension ldx), out[1] = the same of Y: one block, fixed order.
+// (single-term gate: X = slab product with the residual term, Y = the matching rows of A or B)
+__global__ void __launch_bounds__(256)
+slab_sumsq(const float* __restrict__ X, long long ldx, const float* __restrict__ Y, long long ldy, int rows, int k, double* __restrict__ out) {
+  __shared__ double rx[256], ry[256];
+  double sx = 0.0, sy = 0.0;
+  for (int o = threadIdx.x; o < rows * k; o += 256) {
+    const int r = o / k, q = o % k;
+    const double x = X[(long long)r * ldx + q], y = Y[(long long)r * ldy + q];
+    sx += x * x;
+    sy += y * y;
+  }
+  rx[threadIdx.x] = sx;
+  ry[threadIdx.x] = sy;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) { rx[threadIdx.x] += rx[threadIdx.x + w]; ry[threadIdx.x] += ry[threadIdx.x + w]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = rx[0]; out[1] = ry[0]; }
+}
+// B[r][q] = colsum[r] * centre[q]  (rows >= n_valid: 0) -- the rank-1 part of R^T G_i, initial value of the reduce target
+__global__ void rank1_init(float* __restrict__ B, long long ldb, long long n_rows, long long n_valid, int k,
+                           const float* __restrict__ colsum, const float* __restrict__ centre) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * k) return;
+  const long long r = idx / k;
+  const int q = (int)(idx % k);
+  B[r * ldb + q] = (r < n_valid) ? colsum[r] * centre[q] : 0.f;
+}
+// First-order restoration of the residual term in the backbone solve: part[chunk][a][b] = sum_r B[r][a] * lo[r][b],
+// lo[r][b] = (G[r][b] - centre[b]) - Gs[r][b]  (exact in fp32).  The correction is 2^-9 of M, so fp32 accumulation per
+// chunk (and fp64 across chunks) is ample.  grid = (chunks, ceil(ka/64), ceil(kb/64)), 256 threads, 4x4 per thread.
+__global__ void __launch_bounds__(256)
+corr_partial(const float* __restrict__ B, long long ldb, const float* __restrict__ G, long long ldg,
+             const __nv_bfloat16* __restrict__ Gs, long long ldgs, const float* __restrict__ centre, double* __restrict__ part,
+             long long n_rows, int ka, int kb, int rows_per_chunk) {
+  __shared__ float Xs[16][64 + 4];
+  __shared__ float Ys[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int a0 = blockIdx.y * 64, b0 = blockIdx.z * 64;
+  const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
+  const long long r_end = min(n_rows, r_begin + rows_per_chunk);
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      const int rr = idx / 64, cc = idx % 64;
+      float xv = 0.f, yv = 0.f;
+      if (r0 + rr < r_end) {
+        if (a0 + cc < ka) xv = B[(r0 + rr) * ldb + a0 + cc];
+        if (b0 + cc < kb) yv = (G[(r0 + rr) * ldg + b0 + cc] - centre[b0 + cc]) - __bfloat162float(Gs[(r0 + rr) * ldgs + b0 + cc]);
+      }
+      Xs[rr][cc] = xv;
+      Ys[rr][cc] = yv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Xs[rr][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ys[rr][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double* out = part + (long long)blockIdx.x * ka * kb;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = a0 + ty * 4 + i;
+    if (a >= ka) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = b0 + tx * 4 + j;
+      if (b < kb) out[(long long)a * kb + b] = (double)acc[i][j];
+    }
   }
 }
 
@@ -707,12 +856,6 @@ __global__ void fill_hashed_uniform(OT* __restrict__ dst, long long ld, long lon
   if (idx >= rows * cols) return;
   const long long r = idx / cols, c = idx % cols;
   dst[r * ld + c] = cast_out<OT>(hashed_uniform(seed, (unsigned long long)((row0 + r) * cols + c)));
-}
-
-template <class T>
-__global__ void fill_value(T* p, long long n, T v) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
 }
 
 }  // namespace fz

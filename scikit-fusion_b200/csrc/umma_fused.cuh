@@ -38,6 +38,8 @@ struct FusedParams {
   int b_terms;         // split terms multiplied in the B-product: 2 (default) or 1 = first term only (N = 64; validated, unused by
                        // the engine: see DESIGN.md section 4).  An fp16 first term is NOT possible: kind::f16 with a bf16 A operand
                        // and an fp16 B operand raises an illegal-instruction exception on sm_100a (profiles/r01b_mixed_format_probe.log)
+  const float* rowsum = nullptr;   // mean-centred operand form (G = 1 c^T + D, the split terms represent D): row sums of R, and
+  const float* cj = nullptr;       // the centre of the column factor; A += rowsum c_j^T in the epilogue (nullptr: plain form)
   int probe_skip_flush;// developer probe only (wrong results): bit0 = no reductions, bit1 = no B-product MMAs, bit2 = no A-product MMAs,
                        // bit4 = B-product with the first split term only (N = 64), bit5 = A-product likewise: what a 1.5- / 1-term
                        // operand form would cost (profiles/r01b_sustained_term_count_study.log)
@@ -291,9 +293,11 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
     if (n_tiles > 0) {
       ptx::mbar_wait(aacc_full, 0);
       ptx::tc_fence_after();
+      const bool rank1 = (p.rowsum != nullptr) && (blockIdx.y == 0);
       for (int t = 0; t < 2; ++t) {
         const int arow = r0 + t * kFuTile + lrow;
         float* out = (arow < p.n_rows) ? p.A + (long long)arow * p.lda : nullptr;
+        const float rs = (rank1 && out != nullptr) ? p.rowsum[arow] : 0.f;
 #pragma unroll
         for (int q0 = 0; q0 < 64; q0 += 32) {
           float hi[32], lo[32];
@@ -304,7 +308,8 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (q0 + i < p.k_a) {
-                const float v = hi[i] + lo[i];
+                float v = hi[i] + lo[i];
+                if (rank1) v = fmaf(rs, __ldg(p.cj + q0 + i), v);
                 if (p.a_atomic) atomicAdd(out + q0 + i, v);
                 else out[q0 + i] = v;
               }

@@ -17,11 +17,12 @@ CSRC = os.path.join(PKG_ROOT, "csrc")
 FZ_F64, FZ_F32, FZ_BF16, FZ_U8 = 0, 1, 2, 3
 FZ_HOST, FZ_DEVICE = 0, 1
 FZ_DFMF, FZ_DFMC = 0, 1
+FZ_TERMS_AUTO, FZ_TERMS_CENTRED1 = 0, -1
 
 # every symbol include/fz_fusion.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "fz_create", "fz_destroy", "fz_last_error", "fz_version", "fz_launch_count", "fz_set_shard", "fz_add_type",
-    "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_finalize", "fz_iterate",
+    "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_operand_stats", "fz_finalize", "fz_iterate",
     "fz_phase_products", "fz_phase_update", "fz_phase_products_begin", "fz_phase_product_relation", "fz_phase_products_end", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
     "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete",
     "fz_fill_uniform", "fz_profile", "fz_profile_read",
@@ -84,6 +85,7 @@ def lib():
         "fz_set_factor": (i32, [vp, i32, vp, i64, i32, i32]),
         "fz_set_backbone": (i32, [vp, i32, vp, i64, i32, i32]),
         "fz_set_split_terms": (i32, [vp, i32]),
+        "fz_operand_stats": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
         "fz_finalize": (i32, [vp]),
         "fz_iterate": (i32, [vp, i32, i32, vp]),
         "fz_phase_products": (i32, [vp, i32, vp]),
@@ -274,7 +276,17 @@ class Engine(object):
         keep, ptr, ld, code, mem = _describe(S)
         self._ck(self._L.fz_set_backbone(self._h, rel, ptr, ld, code, mem))
 
+    def operand_stats(self):
+        """{single, two_term: dfmf iterations run with each fused kernel; err, cond: last gate measurement}."""
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        e, c = ctypes.c_double(0), ctypes.c_double(0)
+        self._ck(self._L.fz_operand_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(e), ctypes.byref(c)))
+        return {"single": a.value, "two_term": b.value, "err": e.value, "cond": c.value}
+
     def set_split_terms(self, terms):
+        """1..3 (plain operand form), 'auto' / 0 (centred form, kernel chosen per iteration from a measured error
+        estimate) or 'centred1' / -1 (always the single-term kernel); include/fz_fusion.h."""
+        terms = {"auto": FZ_TERMS_AUTO, "centred1": FZ_TERMS_CENTRED1}.get(terms, terms)
         self._ck(self._L.fz_set_split_terms(self._h, int(terms)))
 
     def finalize(self):

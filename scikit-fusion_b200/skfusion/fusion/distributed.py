@@ -154,7 +154,7 @@ def local_rows(n, world, rank):
 def build_sharded_engine(R_local, sizes, ranks, obj_types, G0, world, rank, device, opts):
     """Engine for this rank: global type sizes, local row blocks of the relations, full initial factors."""
     eng = _capi.Engine(device=device, compute=opts.get("dtype", "float32"))
-    if opts.get("split_terms"):
+    if opts.get("split_terms") is not None:
         eng.set_split_terms(opts["split_terms"])
     eng.set_shard(world, rank)
     tid = {t: eng.add_type(sizes[t], int(ranks[t])) for t in obj_types}

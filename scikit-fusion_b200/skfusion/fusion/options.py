@@ -10,7 +10,9 @@ Defaults can be changed process-wide (``engine_options.update(dtype='float64')``
                where B200's fp64 rate makes exactness free, and float32 beyond -- or whenever storage is bfloat16.
   storage      device dtype of relation matrices: None (= dtype), or 'bfloat16' to take the
                tcgen05 tensor-core path (rank <= 64, fp32 engine)
-  split_terms  bf16 terms used to represent a factor on the tensor-core path (1..3)
+  split_terms  operand form of the factors on the tensor-core path: 1..3 bf16 terms of the factor itself, or 'auto' --
+               the mean-centred form with the single-term / two-term kernel chosen per iteration from a measured error
+               estimate (include/fz_fusion.h: FZ_TERMS_AUTO) -- or 'centred1' (always the single-term kernel)
   device_init  where the data-driven initialisations (random_c / random_vcol) compute their column means: 'auto'
                (default: on the GPU when a relation is already device-resident or the graph has more than
                AUTO_FP64_MAX_ENTRIES entries, otherwise with numpy on the host exactly like the reference), True, False.
@@ -18,11 +20,15 @@ Defaults can be changed process-wide (``engine_options.update(dtype='float64')``
 """
 import os
 
+def _terms(text):
+    return text if text in ("auto", "centred1") else int(text)
+
+
 engine_options = {
     "device": int(os.environ.get("SKFUSION_B200_DEVICE", "0")),
     "dtype": os.environ.get("SKFUSION_B200_DTYPE", "auto"),
     "storage": os.environ.get("SKFUSION_B200_STORAGE") or None,
-    "split_terms": int(os.environ.get("SKFUSION_B200_SPLIT_TERMS", "2")),
+    "split_terms": _terms(os.environ.get("SKFUSION_B200_SPLIT_TERMS", "2")),
     "device_init": {"1": True, "0": False}.get(os.environ.get("SKFUSION_B200_DEVICE_INIT", ""), "auto"),
 }
 

@@ -47,7 +47,7 @@ class _Problem(object):
     def __init__(self, opts):
         self.opts = opts
         self.engine = _capi.Engine(device=opts["device"], compute=opts["dtype"])
-        if opts.get("split_terms"):
+        if opts.get("split_terms") is not None:
             self.engine.set_split_terms(opts["split_terms"])
         self.type_id = {}
         self.type_order = []

@@ -22,6 +22,7 @@ PKG = "_skfusion_reference"
 
 
 def available():
+    """REF_ROOT may be repointed (module attribute) before the first load(), e.g. at baseline/_ref on the GPU box."""
     return os.path.isdir(os.path.join(REF_ROOT, "skfusion", "fusion"))
 
 

@@ -1,5 +1,5 @@
-"""bench.py's reference arm runs on the CPU (the oracle port on a bounded sample) and prints ONE JSON line with the
-contract's keys; checked here with a tiny sample so the CPU suite stays fast.  The GPU arm's line is recorded under
+"""bench.py's reference arm runs on the CPU (the reference's dfmf from baseline/_ref, else its oracle port, on bounded
+samples) and prints ONE JSON line with the contract's keys; checked here with tiny samples so the CPU suite stays fast.  The GPU arm's line is recorded under
 profiles/ (it needs a B200)."""
 import json
 import os
@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                          "--cpu-n", "256"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--cpu-sizes", "128,256"], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env=dict(os.environ, OMP_NUM_THREADS="1"))     # what torch.distributed.run exports to its workers
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -19,7 +20,11 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "it/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("DFMF iterations/sec")
     assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "n=256" in d["cpu_baseline"]["sample"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and "n=256" in cb["sample"]
+    assert cb["kind"] == ("reference" if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "skfusion")) else "port")
+    assert cb["cores"] == min(os.cpu_count(), 64) or cb["cores"] == os.cpu_count()    # the BLAS pool is widened past OMP_NUM_THREADS=1
+    assert [p["n"] for p in cb["points"]] == [128, 256] and cb["largest_measured"]["n"] == 256 and "max_rel_residual" in cb["fit"]
     assert d["e2e"] == {"value": d["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["n_per_type"] == 81920 and d["config"]["rank"] == 64 and d["config"]["relations"] == 10
 
@@ -27,7 +32,7 @@ def test_reference_arm_prints_the_contract_line():
 def test_other_ranks_of_the_reference_arm_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-                          "--warmup", "1", "--cpu-n", "256"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+                          "--warmup", "1", "--cpu-sizes", "128,256"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
