@@ -20,6 +20,7 @@
  *     _dfmc.py:268).  Outputs are written into caller-owned buffers.
  *   - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*; NULL =
  *     the legacy default stream).  Calls that return data to the HOST synchronise that stream.
+ *   - every call makes the handle's device current for its duration and restores the caller's device.
  *   - row sharding (one process per GPU): fz_set_shard(world, rank) before any fz_add_type.  Type t
  *     then owns rows [rank*m_t, (rank+1)*m_t) with m_t = ceil(n_t/world); relation (i,j) is given as
  *     the row block of type i's local rows; the iteration is split into fz_phase_* calls and the
@@ -59,6 +60,18 @@ int64_t fz_launch_count(const fz_engine* e);
 
 /* ---- problem description (reference: the R / Theta / M dicts, dfmf.py:69-85, dfmc.py:69-94) ---- */
 int fz_set_shard(fz_engine* e, int world, int rank);
+/* Collectives inside the library (NCCL over NVLink, resolved at run time from libnccl.so.2).  Every rank of the shard group
+ * calls fz_comm_init with the same 128-byte id from fz_comm_unique_id -- each from its own process (one process per GPU:
+ * rank 0 makes the id, the host broadcasts it) or its own thread -- any time after fz_set_shard.  fz_iterate and
+ * fz_objective on such a handle then run the whole sharded iteration, collectives included, and fz_phase_* / fz_comm_small
+ * ... are not needed.  Replaces the reference's only parallelism, the joblib fan-out (_dfmf.py:69-73, dfmf.py:87-95). */
+int fz_comm_unique_id(void* out128);
+int fz_comm_init(fz_engine* e, const void* unique_id128);
+/* One process driving several GPUs: the n handles form one shard group (rank i on handle i, each created on its own device).
+ * The calls below run the per-handle call on one host thread per handle and return when all have finished. */
+int fz_group_comm_init(fz_engine** engines, int n);
+int fz_group_iterate(fz_engine** engines, int n, int algo, int n_iters);      /* fz_iterate on the NULL stream + synchronise */
+int fz_group_objective(fz_engine** engines, int n, double* per_relation, double* total);
 /* returns the type id (>= 0).  n = number of objects (global), k = factorization rank. */
 int fz_add_type(fz_engine* e, int64_t n, int k);
 /* Relation between row type ti and column type tj; ti == tj declares a constraint matrix Theta_t.
@@ -91,7 +104,7 @@ int fz_finalize(fz_engine* e);
 
 /* ---- the hot loop --------------------------------------------------------------------------- */
 /* n_iters iterations of the multiplicative-update loop (_dfmf.py:212-296 / _dfmc.py:270-366).
- * Unsharded handles only (sharded handles use the phases below). */
+ * Sharded handles need fz_comm_init (the engine then runs the collectives) or the phase calls below. */
 int fz_iterate(fz_engine* e, int algo, int n_iters, void* stream);
 /* Sharded iteration, in order:  products -> [all-reduce small, reduce-scatter B] -> update ->
  * [all-gather factors].  fz_iterate == products + update when world == 1. */

@@ -499,23 +499,23 @@ static int run_fused1_case(int rows, int cols, int ka, int kb, int csplit, int t
   CK(cudaMemset(dA, 0, (size_t)rows * ka * 4));
   if (rank1) rank1_init<<<(unsigned)(((size_t)cols * kb + 255) / 256), 256>>>(dB, kb, cols, cols, kb, dCs, dCi);
   else CK(cudaMemset(dB, 0, (size_t)cols * kb * 4));
-  CUtensorMap tr, tgj, tgi, tb; std::string err;
-  if (kb % 4 != 0 || kb < 32) tma_flush = 0;
+  CUtensorMap tr, tgj, tgi, tb, ta; std::string err;
+  int flush_b = tma_flush, flush_a = tma_flush;
+  if (kb % 4 != 0 || kb < 32) flush_b = 0;
+  if (ka % 4 != 0 || ka < 32 || rows < 32) flush_a = 0;
   bool ok = make_tmap_bf16_2d(&tr, dX, rows, cols, ld, 64, 128, &err) && make_tmap_bf16_2d(&tgj, dGj, cols, N, N, 64, 128, &err) &&
             make_tmap_bf16_2d(&tgi, dGi, gi_rows, N, N, 64, 128, &err);
-  if (ok && tma_flush) ok = make_tmap_f32_2d(&tb, dB, cols, kb, kb, 32, 32, &err);
-  if (!tma_flush) tb = tr;
+  if (ok && flush_b) ok = make_tmap_f32_2d(&tb, dB, cols, kb, kb, 32, 32, &err);
+  if (ok && flush_a) ok = make_tmap_f32_2d(&ta, dA, rows, ka, ka, 32, 32, &err);
+  if (!flush_b) tb = tr;
+  if (!flush_a) ta = tr;
   if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
   Fused1Params p;
   p.A = dA; p.B = dB; p.lda = ka; p.ldb = kb; p.rowsum = rank1 ? dRs : nullptr; p.cj = dCj; p.n_rows = rows; p.n_cols = cols;
-  p.k_a = ka; p.k_b = kb; p.gi_row0 = gi_row0; p.probe = 0; p.tma_flush = tma_flush;
-  const int tiles = (cols + 127) / 128;
-  p.tiles_per_split = (tiles + csplit - 1) / csplit;
-  const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.a_atomic = splits > 1;
+  p.k_a = ka; p.k_b = kb; p.gi_row0 = gi_row0; p.probe = 0; p.tma_flush = (flush_b ? 1 : 0) | (flush_a ? 2 : 0);
   CK(cudaFuncSetAttribute(umma_fused1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF1SmemBytes));
-  dim3 grid((rows + kF1Blocks * 128 - 1) / (kF1Blocks * 128), splits);
-  umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tgj, tgi, tb, p);
+  const int splits = csplit;       // number of CTAs of the persistent grid
+  umma_fused1_kernel<<<csplit, kF1Threads, kF1SmemBytes>>>(tr, tgj, tgi, tb, ta, p);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> hA((size_t)rows * ka), hB((size_t)cols * kb);
@@ -535,8 +535,8 @@ static int run_fused1_case(int rows, int cols, int ka, int kb, int csplit, int t
       mb = fmax(mb, fabs(s)); eb = fmax(eb, fabs(s - hB[(size_t)c * kb + q]));
     }
   const bool good = ea / ma < 2e-5 && eb / mb < 2e-5;
-  printf("fused1 rows=%d cols=%d ka=%d kb=%d csplit=%d flush=%s gi_row0=%d rank1=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb,
-         splits, tma_flush ? "tma" : "red", gi_row0, (int)rank1, ea / ma, eb / mb, good ? "OK" : "FAIL");
+  printf("fused1 rows=%d cols=%d ka=%d kb=%d ctas=%d flush=%d gi_row0=%d rank1=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb,
+         splits, p.tma_flush, gi_row0, (int)rank1, ea / ma, eb / mb, good ? "OK" : "FAIL");
   cudaFree(dX); cudaFree(dGj); cudaFree(dGi); cudaFree(dA); cudaFree(dB); cudaFree(dRs); cudaFree(dCs); cudaFree(dCj); cudaFree(dCi);
   return good ? 0 : 1;
 }
@@ -552,34 +552,30 @@ static void bench_fused1(int n, int probe, int csplit = 1) {
     fill_random_bf16<<<1184, 256>>>(dX, elems, 1u, 1.0f);
     fill_random_bf16<<<1184, 256>>>(dG, (size_t)n * N, 2u, 1.0f);
   }
-  CUtensorMap tr, tg, tb; std::string err;
+  CUtensorMap tr, tg, tb, ta; std::string err;
   bool ok = make_tmap_bf16_2d(&tr, dX, n, n, n, 64, 128, &err) && make_tmap_bf16_2d(&tg, dG, n, N, N, 64, 128, &err) &&
-            make_tmap_f32_2d(&tb, dB, n, k, k, 32, 32, &err);
+            make_tmap_f32_2d(&tb, dB, n, k, k, 32, 32, &err) && make_tmap_f32_2d(&ta, dA, n, k, k, 32, 32, &err);
   if (!ok) { printf("tmap error: %s\n", err.c_str()); exit(2); }
   CK(cudaFuncSetAttribute(umma_fused1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF1SmemBytes));
   Fused1Params p;
   p.A = dA; p.B = dB; p.lda = k; p.ldb = k; p.rowsum = dRs; p.cj = dC; p.n_rows = n; p.n_cols = n; p.k_a = k; p.k_b = k; p.gi_row0 = 0;
-  p.probe = probe; p.tma_flush = 1;
-  const int tiles = (n + 127) / 128;
-  p.tiles_per_split = (tiles + csplit - 1) / csplit;
-  const int splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.a_atomic = splits > 1;
-  dim3 grid((n + kF1Blocks * 128 - 1) / (kF1Blocks * 128), splits);
+  p.probe = probe; p.tma_flush = 3;
+  dim3 grid(csplit > 0 ? csplit : 148);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  for (int w = 0; w < 2; ++w) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, p);
+  for (int w = 0; w < 2; ++w) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, ta, p);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   int reps = 40;
   float ms;
   if (g_sustain_s > 0) {
     reps = (int)(g_sustain_s * 0.5 / 0.6e-3);
-    for (int r = 0; r < reps; ++r) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, p);
+    for (int r = 0; r < reps; ++r) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, ta, p);
   }
   CK(cudaEventRecord(e0));
-  for (int r = 0; r < reps; ++r) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, p);
+  for (int r = 0; r < reps; ++r) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, ta, p);
   CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
   CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
-  printf("bench FUSED1 probe=%d n=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s executed\n", probe, n, grid.x, grid.y,
+  printf("bench FUSED1 (persistent) probe=%d n=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s executed\n", probe, n, grid.x, grid.y,
          ms, elems * 2.0 / 1e9 / (ms * 1e-3), 2.0 * 2.0 * elems * 64 / (ms * 1e-3) / 1e12);
   cudaFree(dX); cudaFree(dG); cudaFree(dA); cudaFree(dB); cudaFree(dRs); cudaFree(dC);
 }
@@ -588,18 +584,20 @@ static int main_fused1(int nbench, double sustain, int csplit) {
   int fails = 0;
   fails += run_fused1_case(128, 128, 64, 64, 1);
   fails += run_fused1_case(512, 384, 64, 64, 1);
-  fails += run_fused1_case(640, 256, 64, 64, 1);                 // second CTA holds one row block only
-  fails += run_fused1_case(1000, 520, 64, 40, 1);
-  fails += run_fused1_case(520, 1000, 50, 64, 3);
+  fails += run_fused1_case(640, 256, 64, 64, 1);                 // one CTA, two segments (second row group: one row block)
+  fails += run_fused1_case(640, 256, 64, 64, 3);                 // 4 units over 3 CTAs
+  fails += run_fused1_case(1000, 520, 64, 40, 2);
+  fails += run_fused1_case(520, 1000, 50, 64, 5);
   fails += run_fused1_case(130, 77, 7, 12, 1);                    // red.global fallback, boxes larger than the tensors
-  fails += run_fused1_case(2048, 4096, 64, 64, 4);
+  fails += run_fused1_case(2048, 4096, 64, 64, 7);                // row groups split between CTAs at odd tiles
   fails += run_fused1_case(1000, 520, 64, 40, 1, 0);
-  fails += run_fused1_case(3000, 2100, 33, 36, 2);
-  fails += run_fused1_case(777, 3001, 64, 64, 1);
+  fails += run_fused1_case(3000, 2100, 33, 36, 148);              // more CTAs than units: idle CTAs
+  fails += run_fused1_case(777, 3001, 64, 64, 13);
   fails += run_fused1_case(777, 1001, 64, 64, 2, 1, 1024);        // sharded: factor rows offset
   fails += run_fused1_case(500, 1001, 64, 48, 1, 1, 12500);
-  fails += run_fused1_case(1000, 520, 64, 40, 1, 1, 0, false);    // no rank-1 part
-  fails += run_fused1_case(4096, 8192, 64, 64, 8);
+  fails += run_fused1_case(1000, 520, 64, 40, 4, 1, 0, false);    // no rank-1 part
+  fails += run_fused1_case(4096, 8192, 64, 64, 148);
+  fails += run_fused1_case(5000, 3000, 64, 64, 37);
   printf("fused1 correctness: %d failing cases\n", fails);
   if (nbench > 0) {
     g_sustain_s = 0;
@@ -615,7 +613,7 @@ static int main_fused1(int nbench, double sustain, int csplit) {
 
 int main(int argc, char** argv) {
   setvbuf(stdout, nullptr, _IONBF, 0);
-  if (argc > 1 && argv[1][0] == '1') return main_fused1(argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atof(argv[3]) : 0.0, argc > 4 ? atoi(argv[4]) : 2);
+  if (argc > 1 && argv[1][0] == '1') return main_fused1(argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atof(argv[3]) : 0.0, argc > 4 ? atoi(argv[4]) : 148);
   if (argc > 1 && argv[1][0] == 'm') {   // single-term B-product (the fp16 variant of this probe hit an illegal instruction:
     int fails = 0;                       //  bf16 A x fp16 B is not a legal kind::f16 combination, profiles/r01b_mixed_format_probe.log)
     fails += run_fused_case(512, 384, 64, 64, 1, 1, 1);

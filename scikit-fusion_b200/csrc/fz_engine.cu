@@ -19,11 +19,13 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/fz_fusion.h"
 #include "fz_chain.cuh"
 #include "fz_kernels.cuh"
+#include "nccl_shim.h"
 #include "tmap.h"
 #include "umma_fused.cuh"
 #include "umma_fused1.cuh"
@@ -41,6 +43,11 @@ struct FzError {
     char buf_[512];                                    \
     snprintf(buf_, sizeof(buf_), __VA_ARGS__);         \
     throw FzError{(st), std::string(buf_)};            \
+  } while (0)
+#define NCCL_OK(x)                                                                                       \
+  do {                                                                                                   \
+    ncclResult_t r_ = (x);                                                                               \
+    if (r_ != ncclSuccess) FZ_THROW(FZ_ERR_CUDA, "%s failed: %s (%s:%d)", #x, nccl_api().GetErrorString(r_), __FILE__, __LINE__); \
   } while (0)
 #define CUDA_OK(x)                                                                                 \
   do {                                                                                             \
@@ -122,8 +129,10 @@ class EngineBase {
     prof_bytes += bytes;
     prof_alg_bytes += bytes / products_per_pass;   // 2: single-product launch (half credit); 1: fused launch
   }
+  int device = 0;              // every C-ABI entry makes this the calling thread's current device (DeviceGuard)
   virtual int compute_dtype() const = 0;
   virtual void set_shard(int world, int rank) = 0;
+  virtual void comm_init(const void* unique_id) = 0;
   virtual int add_type(int64_t n, int k) = 0;
   virtual int add_relation(int ti, int tj, const void* data, int64_t ld, int src, int mem, int storage, int borrow,
                            const uint8_t* mask, int64_t mask_ld, int mask_mem) = 0;
@@ -278,8 +287,8 @@ class Engine : public EngineBase {
     int m_chunks = 0, m_rows_per_chunk = 0;
     DevBuf S, t2, t5, W1, W4, work;
     bool has_backbone = false;
-    CUtensorMap tmX, tmXT, tmEs, tmB;
-    bool has_tmB = false;
+    CUtensorMap tmX, tmXT, tmEs, tmB, tmA;
+    bool has_tmB = false, has_tmA = false;
     DevBuf rowsum, colsum;       // centred operand form: row / column sums of the stored relation (fp32), computed once
     bool sums_ready = false;
     int corr_chunks = 0, corr_rows_per_chunk = 0;   // first-order correction of M (single-term form): extra slots of M_part
@@ -289,6 +298,14 @@ class Engine : public EngineBase {
 
   int device_;
   int world_ = 1, rank_ = 0;
+  // ---- collectives inside the library (fz_comm_init): NCCL on its own stream, ordered against the products by events
+  ncclComm_t comm_ = nullptr;
+  cudaStream_t comm_stream_ = nullptr;
+  cudaEvent_t ev_c0_ = nullptr, ev_c1_ = nullptr, ev_gram_ = nullptr, ev_gram_done_ = nullptr;
+  std::vector<cudaEvent_t> ev_upd_, ev_gather_;
+  std::vector<char> gather_pending_;
+  int64_t gram_count_ = 0;      // leading doubles of small_ that hold the Gram sums (all-reduced ahead of the rest)
+  bool pinv_done_ = false;      // this iteration's pseudo-inverses already ran beside the products
   int terms_ = 2;           // split terms of the factor operand: 1..3 plain form; FZ_TERMS_AUTO / FZ_TERMS_CENTRED1: centred form
   int gs_terms_ = 2;        // terms stored in Gs (the centred forms always keep [hi | lo])
   bool centred_ = false;    // mean-centred operand form for the fused dfmf products (terms_ <= 0)
@@ -335,8 +352,13 @@ class Engine : public EngineBase {
   std::vector<int> tf_sum_types_;
 
  public:
-  explicit Engine(int device) : device_(device) {}
+  explicit Engine(int device) : device_(device) { this->device = device; }
   ~Engine() override {
+    if (comm_) nccl_api().CommDestroy(comm_);
+    if (comm_stream_) cudaStreamDestroy(comm_stream_);
+    for (auto e : {ev_c0_, ev_c1_, ev_gram_, ev_gram_done_}) if (e) cudaEventDestroy(e);
+    for (auto e : ev_upd_) cudaEventDestroy(e);
+    for (auto e : ev_gather_) cudaEventDestroy(e);
     if (aux_) cudaStreamDestroy(aux_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
@@ -353,6 +375,21 @@ class Engine : public EngineBase {
     if (world < 1 || rank < 0 || rank >= world) FZ_THROW(FZ_ERR_INVALID, "bad shard %d/%d", rank, world);
     world_ = world;
     rank_ = rank;
+  }
+
+  // One communicator per handle; every rank of the shard group calls this with the same id (fz_comm_unique_id), each from
+  // its own process or thread.  From then on fz_iterate / fz_objective run the collectives themselves.
+  void comm_init(const void* unique_id) override {
+    if (world_ < 2) FZ_THROW(FZ_ERR_INVALID, "fz_comm_init needs a sharded handle (fz_set_shard with world > 1)");
+    if (comm_) FZ_THROW(FZ_ERR_INVALID, "communicator already initialised");
+    if (unique_id == nullptr) FZ_THROW(FZ_ERR_INVALID, "null unique id");
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) FZ_THROW(FZ_ERR_UNSUPPORTED, "NCCL unavailable: %s", nc.error.c_str());
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    NCCL_OK(nc.CommInitRank(&comm_, world_, id, rank_));
+    CUDA_OK(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&ev_c0_, &ev_c1_, &ev_gram_, &ev_gram_done_}) CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
 
   int add_type(int64_t n, int k) override {
@@ -468,6 +505,7 @@ class Engine : public EngineBase {
     for (auto& t : types_) small_count_ += (int64_t)t->k * t->k;
     for (auto& r : rels_)
       if (!r->theta) small_count_ += (int64_t)types_[r->ti]->k * types_[r->tj]->k;
+    for (auto& t : types_) gram_count_ += (int64_t)t->k * t->k;
     int64_t gate_off = small_count_;
     if (centred_ && terms_ == FZ_TERMS_AUTO) {
       for (auto& r : rels_)
@@ -554,6 +592,8 @@ class Engine : public EngineBase {
         // reduce target of the fused kernel's TMA flush (fp32, box 32 x 32, 128B swizzle)
         if (kDT == FZ_F32 && (Ti.k % 4) == 0 && Ti.k >= 32)
           r.has_tmB = make_tmap_f32_2d(&r.tmB, r.B.p, (uint64_t)Tj.n_pad, (uint64_t)Ti.k, (uint64_t)Ti.k, 32, 32, &e);
+        if (kDT == FZ_F32 && centred_ && (Tj.k % 4) == 0 && Tj.k >= 32 && r.rows_loc >= 32)   // A reduce target of the single-term kernel
+          r.has_tmA = make_tmap_f32_2d(&r.tmA, r.A.p, (uint64_t)r.rows_loc, (uint64_t)Tj.k, (uint64_t)Tj.k, 32, 32, &e);
         // v4 boxes are {64, 256} on the relation and {16, 64} on B: relations smaller than a box keep the v3 kernel
         if (fused_ver_ == 4 && kDT == FZ_F32 && r.rows_loc >= 256 && r.cols >= 64 && Ti.GsT.p != nullptr && Tj.GsT.p != nullptr) {
           r.v4_ok = make_tmap_2d(&r.tmX256, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols,
@@ -578,9 +618,14 @@ class Engine : public EngineBase {
       CUDA_OK(cudaStreamCreateWithFlags(&aux_, cudaStreamNonBlocking));
       CUDA_OK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
       CUDA_OK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
-      ev_rel_.resize(rels_.size());
-      for (auto& e : ev_rel_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    ev_rel_.resize(rels_.size());
+    for (auto& e : ev_rel_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_upd_.resize(types_.size());
+    ev_gather_.resize(types_.size());
+    gather_pending_.assign(types_.size(), 0);
+    for (auto& e : ev_upd_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ev_gather_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     gate_enabled_ = centred_ && terms_ == FZ_TERMS_AUTO && !graph_worthwhile();   // small graphs are launch-bound: nothing to gain
     build_job_tables();
     // opt in to the large dynamic shared memory of the tensor-core kernels
@@ -592,7 +637,12 @@ class Engine : public EngineBase {
   // ---------------------------------------------------------------------------------------------
   void iterate(int algo, int n_iters, cudaStream_t st) override {
     need_final();
-    if (world_ != 1) FZ_THROW(FZ_ERR_INVALID, "fz_iterate is for unsharded handles; use the fz_phase_* calls");
+    if (world_ != 1) {
+      if (!comm_) FZ_THROW(FZ_ERR_INVALID, "fz_iterate on a sharded handle needs fz_comm_init (or drive the fz_phase_* calls)");
+      for (int it = 0; it < n_iters; ++it) run_one_sharded(algo, st);
+      wait_gathers(st);
+      return;
+    }
     int done = 0;
     // Small graphs are launch-latency-bound (tens of kernels of a few microseconds each): after one eager
     // iteration, two iterations (the factor double-buffer has period two) are captured into a CUDA graph and
@@ -640,6 +690,36 @@ class Engine : public EngineBase {
     phase_products(algo, st);
     phase_update(algo, st);
   }
+  // One sharded iteration with the collectives on the communicator's stream: the reduce-scatter of relation
+  // r's B partial runs under the streamed products of relation r+1, the Gram all-reduce and the pseudo-inverses under the
+  // first products, the all-gather of type t's new factor under the update of type t+1.
+  void run_one_sharded(int algo, cudaStream_t st) {
+    if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_UNSUPPORTED, "sharded handles run dfmf (dfmc and transform are replicas)");
+    const NcclApi& nc = nccl_api();
+    const ncclDataType_t dt = (kDT == FZ_F32) ? ncclFloat32 : ncclFloat64;
+    phase_products_begin(algo, st);
+    for (size_t r = 0; r < rels_.size(); ++r) {
+      phase_product_relation(algo, (int)r, st);
+      RelRec& rel = *rels_[r];
+      if (rel.theta) continue;
+      CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_rel_[r], 0));            // this relation's B partial is complete
+      NCCL_OK(nc.ReduceScatter(rel.B.p, rel.Bloc.p, (size_t)types_[rel.tj]->m_loc * types_[rel.ti]->k, dt, ncclSum, comm_, comm_stream_));
+    }
+    phase_products_end(algo, st);                                          // joins the fp64 reductions into st
+    CUDA_OK(cudaEventRecord(ev_c0_, st));
+    CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
+    const int64_t first = pinv_done_ ? gram_count_ : 0;                    // the Gram sums went ahead (phase_products_begin)
+    if (small_count_ > first)
+      NCCL_OK(nc.AllReduce(small_.template as<double>() + first, small_.template as<double>() + first, (size_t)(small_count_ - first),
+                           ncclFloat64, ncclSum, comm_, comm_stream_));
+    CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
+    CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));                           // every reduce-scatter and the all-reduce have landed
+    phase_update(algo, st);
+  }
+  void wait_gathers(cudaStream_t st) {
+    for (size_t t = 0; t < gather_pending_.size(); ++t)
+      if (gather_pending_[t]) { CUDA_OK(cudaStreamWaitEvent(st, ev_gather_[t], 0)); gather_pending_[t] = 0; }
+  }
   // worth a graph when the relations are small enough that launch latency, not bandwidth, sets the pace
   bool graph_worthwhile() const {
     double entries = 0.0;
@@ -679,13 +759,29 @@ class Engine : public EngineBase {
     if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_UNSUPPORTED, "piecewise products are for dfmf");
     single_now_ = centred_ && choose_single();
     gate_check_now_ = gate_enabled_ && (it_count_ < 4 || (it_count_ % 8) == 0);
+    wait_gathers(st);                                  // the factors updated by the previous iteration are whole again
     if (gate_slot_count_ > 0) CUDA_OK(cudaMemsetAsync(gate_slots_, 0, (size_t)gate_slot_count_ * 8, st));
+    pinv_done_ = false;
     if (!use_aux_) { grams(st, centred_); return; }
     for (auto& tp : types_)
       if (tp->need_gs) split(*tp, st, centred_);       // operand forms first: every streamed product needs them
     CUDA_OK(cudaEventRecord(ev_fork_, st));
     CUDA_OK(cudaStreamWaitEvent(aux_, ev_fork_, 0));
     for (auto& tp : types_) gram_of(*tp, aux_);        // Gram matrices beside the first streamed products
+    if (world_ == 1 || comm_) {
+      // The pseudo-inverses depend on the Gram sums only: run them now, under the streamed products, instead of in the
+      // serial tail behind the last product (sharded: their all-reduce goes ahead of the relations' reduce-scatters).
+      if (comm_) {
+        CUDA_OK(cudaEventRecord(ev_gram_, aux_));
+        CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_gram_, 0));
+        NCCL_OK(nccl_api().AllReduce(small_.p, small_.p, (size_t)gram_count_, ncclFloat64, ncclSum, comm_, comm_stream_));
+        CUDA_OK(cudaEventRecord(ev_gram_done_, comm_stream_));
+        CUDA_OK(cudaStreamWaitEvent(aux_, ev_gram_done_, 0));
+      }
+      pinv_spd<<<(unsigned)types_.size(), kChainThreads, kChainSmemBytes, aux_>>>(pinv_jobs_.template as<PinvJob>());
+      ++launches;
+      pinv_done_ = true;
+    }
   }
   void phase_product_relation(int algo, int rel, cudaStream_t st) override {
     (void)algo;
@@ -695,8 +791,8 @@ class Engine : public EngineBase {
       product_A(r, st);
       product_B(r, st);
     }
+    CUDA_OK(cudaEventRecord(ev_rel_[rel], st));        // A_ij and the B partial are complete here
     if (!use_aux_) { reduce_M(r, st); if (gate_check_now_) gate_measure(r, rel, st); return; }
-    CUDA_OK(cudaEventRecord(ev_rel_[rel], st));        // A_ij is complete here
     CUDA_OK(cudaStreamWaitEvent(aux_, ev_rel_[rel], 0));
     reduce_M(r, aux_);                                 // G_i^T A_ij overlaps the next relation's stream
     if (gate_check_now_) gate_measure(r, rel, aux_);
@@ -741,7 +837,18 @@ class Engine : public EngineBase {
       }
       theta_products(st);
     }
-    for (size_t t = 0; t < types_.size(); ++t) update_type((int)t, dfmf ? 1 : 0, st);
+    for (size_t t = 0; t < types_.size(); ++t) {
+      update_type((int)t, dfmf ? 1 : 0, st);
+      if (comm_) {       // rows of the new factor go round while the next type updates (in-place all-gather)
+        TypeRec& Tt = *types_[t];
+        CUDA_OK(cudaEventRecord(ev_upd_[t], st));
+        CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_upd_[t], 0));
+        NCCL_OK(nccl_api().AllGather(nxt(Tt) + Tt.row0 * Tt.k, nxt(Tt), (size_t)Tt.m_loc * Tt.k, (kDT == FZ_F32) ? ncclFloat32 : ncclFloat64,
+                                     comm_, comm_stream_));
+        CUDA_OK(cudaEventRecord(ev_gather_[t], comm_stream_));
+        gather_pending_[t] = 1;
+      }
+    }
     for (auto& tp : types_) tp->cur ^= 1;
     CUDA_OK(cudaGetLastError());
   }
@@ -836,6 +943,7 @@ class Engine : public EngineBase {
     need_final();
     if (t < 0 || t >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id %d", t);
     TypeRec& Tt = *types_[t];
+    wait_gathers(st);
     copy_out(Tt.G[Tt.cur].p, Tt.k, kDT, dst, ld, dd, mem, Tt.n, Tt.k, st);
   }
   void get_backbone(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) override {
@@ -845,33 +953,51 @@ class Engine : public EngineBase {
     copy_out(r.S.p, types_[r.tj]->k, FZ_F64, dst, ld, dd, mem, types_[r.ti]->k, types_[r.tj]->k, st);
   }
 
+  // Frobenius residuals ||R - G_i S G_j^T||_F per relation (_dfmf.py:306-319): every relation's squared sum is accumulated
+  // on the device over the local rows, summed over the ranks by one all-reduce when sharded, and read back ONCE.
   void objective(double* per_rel, double* total, cudaStream_t st) override {
     need_final();
-    if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "objective on sharded handles is not implemented");
-    double sum = 0.0;
+    if (world_ != 1 && !comm_) FZ_THROW(FZ_ERR_UNSUPPORTED, "objective on a sharded handle needs fz_comm_init");
+    wait_gathers(st);
+    int n_rel = 0;
+    for (auto& rp : rels_) n_rel += rp->theta ? 0 : 1;
+    if (n_rel == 0) { if (total) *total = 0.0; return; }
+    err_acc_.alloc((size_t)n_rel * 8, false);
+    CUDA_OK(cudaMemsetAsync(err_acc_.p, 0, (size_t)n_rel * 8, st));
     int idx = 0;
     for (auto& rp : rels_) {
       RelRec& r = *rp;
       if (r.theta) continue;
       TypeRec& Ti = *types_[r.ti];
       TypeRec& Tj = *types_[r.tj];
+      double* acc = err_acc_.template as<double>() + idx++;
+      if (r.rows_loc <= 0) continue;
       ensure_T1(r);
-      gemm(cur(Ti), Ti.k, r.W4.template as<T>(), Tj.k, r.T1.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, Ti.k, false, st);
-      CUDA_OK(cudaMemsetAsync(err_acc_.p, 0, 8, st));
+      gemm(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.W4.template as<T>(), Tj.k, r.T1.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, Ti.k, false, st);
       dim3 g(nblk(r.cols, 32), nblk(r.rows_loc, 32));
       if (r.storage == FZ_BF16)
         recon_err<T, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.T1.template as<T>(), Tj.k, cur(Tj),
-                                                       Tj.k, r.rows_loc, r.cols, Tj.k, err_acc_.template as<double>(), nullptr, 0);
+                                                       Tj.k, r.rows_loc, r.cols, Tj.k, acc, nullptr, 0);
       else
         recon_err<T, T><<<g, 256, 0, st>>>((const T*)r.data, r.ld, r.T1.template as<T>(), Tj.k, cur(Tj), Tj.k, r.rows_loc, r.cols,
-                                           Tj.k, err_acc_.template as<double>(), nullptr, 0);
+                                           Tj.k, acc, nullptr, 0);
       ++launches;
-      double sq = 0.0;
-      CUDA_OK(cudaMemcpyAsync(&sq, err_acc_.p, 8, cudaMemcpyDeviceToHost, st));
-      CUDA_OK(cudaStreamSynchronize(st));
-      const double e = std::sqrt(sq);
-      if (per_rel) per_rel[idx] = e;
-      ++idx;
+    }
+    CUDA_OK(cudaGetLastError());
+    if (comm_) {
+      CUDA_OK(cudaEventRecord(ev_c0_, st));
+      CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
+      NCCL_OK(nccl_api().AllReduce(err_acc_.p, err_acc_.p, (size_t)n_rel, ncclFloat64, ncclSum, comm_, comm_stream_));
+      CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
+      CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));
+    }
+    std::vector<double> sq((size_t)n_rel);
+    CUDA_OK(cudaMemcpyAsync(sq.data(), err_acc_.p, (size_t)n_rel * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    double sum = 0.0;
+    for (int i = 0; i < n_rel; ++i) {
+      const double e = std::sqrt(sq[i]);
+      if (per_rel) per_rel[i] = e;
       sum += e;
     }
     if (total) *total = sum;
@@ -1304,8 +1430,11 @@ class Engine : public EngineBase {
       CUDA_OK(cudaStreamSynchronize(st));
       bb_mode_ = mode;
     }
-    pinv_spd<<<(unsigned)types_.size(), kChainThreads, kChainSmemBytes, st>>>(pinv_jobs_.template as<PinvJob>());
-    ++launches;
+    if (!pinv_done_) {
+      pinv_spd<<<(unsigned)types_.size(), kChainThreads, kChainSmemBytes, st>>>(pinv_jobs_.template as<PinvJob>());
+      ++launches;
+    }
+    pinv_done_ = false;
     if (!bb_host_.empty()) {
       backbone_chain<T><<<(unsigned)bb_host_.size(), kChainThreads, kChainSmemBytes, st>>>(bb_jobs_.template as<BackboneJob<T>>());
       ++launches;
@@ -1435,7 +1564,7 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   splits = std::max(1, std::min(splits, tiles));
   p.tiles_per_split = (tiles + splits - 1) / splits;
   splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.a_atomic = splits > 1 ? 1 : 0;
+  p.a_atomic = (splits > 1 || single_now_) ? 1 : 0;     // the single-term kernel always reduces into A
   if (centred_) {    // B starts from the rank-1 part colsum(R) c_i^T of the centred form
     rank1_init<<<nblk(Tj.n_pad * Ti.k, 256), 256, 0, st>>>(r.B.template as<float>(), Ti.k, Tj.n_pad, r.cols, Ti.k, r.colsum.template as<float>(),
                                                            Ti.centre.template as<float>());
@@ -1450,8 +1579,13 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
     Fused1Params q;
     q.A = p.A; q.B = p.B; q.lda = p.lda; q.ldb = p.ldb; q.rowsum = p.rowsum; q.cj = p.cj;
     q.n_rows = p.n_rows; q.n_cols = p.n_cols; q.k_a = p.k_a; q.k_b = p.k_b; q.gi_row0 = p.gi_row0;
-    q.tiles_per_split = p.tiles_per_split; q.a_atomic = p.a_atomic; q.tma_flush = p.tma_flush; q.probe = 0;
-    umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes, st>>>(r.tmX, Tj.tmG128, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX, q);
+    q.tma_flush = (r.has_tmB ? 1 : 0) | (r.has_tmA ? 2 : 0);
+    q.probe = 0;
+    // persistent grid: one CTA per SM, each walking an equal share of the (row group x column tile) units
+    const long long units = (long long)pairs * tiles;
+    const unsigned ctas = (unsigned)std::max<long long>(1, std::min<long long>(sm_count_, units));
+    umma_fused1_kernel<<<ctas, kF1Threads, kF1SmemBytes, st>>>(r.tmX, Tj.tmG128, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX,
+                                                               r.has_tmA ? r.tmA : r.tmX, q);
   } else if (fused_ver_ == 4 && r.v4_ok && !centred_) {
     FusedTParams q;
     q.A = p.A; q.B = p.B; q.lda = p.lda; q.ldb = p.ldb;
@@ -1536,8 +1670,23 @@ struct fz_engine {
   fz::EngineBase* impl;
 };
 
+// Every entry point runs with the handle's device current and restores the caller's device afterwards: a host that
+// drives several GPUs from one process (or torch code that moves the current device) cannot misdirect a launch.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 #define FZ_GUARD(e, body)                                        \
   if (!(e) || !(e)->impl) return FZ_ERR_INVALID;                 \
+  DeviceGuard guard_((e)->impl->device);                         \
   try {                                                          \
     body;                                                        \
   } catch (const fz::FzError& err_) {                            \
@@ -1545,6 +1694,9 @@ struct fz_engine {
     return err_.status;                                          \
   } catch (const std::exception& ex_) {                          \
     (e)->impl->err = ex_.what();                                 \
+    return FZ_ERR_INVALID;                                       \
+  } catch (...) {                                                \
+    (e)->impl->err = "unknown C++ exception";                    \
     return FZ_ERR_INVALID;                                       \
   }                                                              \
   return FZ_OK;
@@ -1593,6 +1745,24 @@ int fill_unknown_impl(XT* X, int64_t ld, int64_t rows, int64_t cols, int mode, d
 }  // namespace
 
 
+// ---- one process driving all the GPUs of the box: one host thread per handle for the duration of the call
+namespace {
+template <class F>
+int for_each_engine(fz_engine** engines, int n, F&& fn) {
+  if (!engines || n <= 0) return FZ_ERR_INVALID;
+  for (int i = 0; i < n; ++i)
+    if (!engines[i] || !engines[i]->impl) return FZ_ERR_INVALID;
+  std::vector<int> rc((size_t)n, FZ_OK);
+  std::vector<std::thread> threads;
+  for (int i = 1; i < n; ++i) threads.emplace_back([&, i] { rc[(size_t)i] = fn(engines[i]); });
+  rc[0] = fn(engines[0]);
+  for (auto& t : threads) t.join();
+  for (int i = 0; i < n; ++i)
+    if (rc[(size_t)i] != FZ_OK) return rc[(size_t)i];
+  return FZ_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int fz_version(void) { return 100; }
@@ -1611,9 +1781,10 @@ int fz_create(fz_engine** out, int device, int compute) {
     fz::g_create_error = "device index out of range";
     return FZ_ERR_INVALID;
   }
-  ce = cudaSetDevice(device);
+  DeviceGuard guard(device);     // the caller's current device is left as it was
+  ce = cudaFree(nullptr);        // context of `device`
   if (ce != cudaSuccess) {
-    fz::g_create_error = std::string("cudaSetDevice failed: ") + cudaGetErrorString(ce);
+    fz::g_create_error = std::string("cannot use device ") + std::to_string(device) + ": " + cudaGetErrorString(ce);
     return FZ_ERR_CUDA;
   }
   cudaDeviceProp prop;
@@ -1636,6 +1807,12 @@ int fz_create(fz_engine** out, int device, int compute) {
 
 int fz_destroy(fz_engine* e) {
   if (!e) return FZ_OK;
+  if (e->impl) {
+    DeviceGuard guard(e->impl->device);
+    delete e->impl;
+    delete e;
+    return FZ_OK;
+  }
   delete e->impl;
   delete e;
   return FZ_OK;
@@ -1650,24 +1827,78 @@ int64_t fz_launch_count(const fz_engine* e) { return (e && e->impl) ? e->impl->l
 
 int fz_set_shard(fz_engine* e, int world, int rank) { FZ_GUARD(e, e->impl->set_shard(world, rank)) }
 
+int fz_comm_unique_id(void* out128) {
+  if (!out128) return FZ_ERR_INVALID;
+  const fz::NcclApi& nc = fz::nccl_api();
+  if (!nc.ok) {
+    fz::g_create_error = "NCCL unavailable: " + nc.error;
+    return FZ_ERR_UNSUPPORTED;
+  }
+  ncclUniqueId id;
+  if (nc.GetUniqueId(&id) != ncclSuccess) {
+    fz::g_create_error = "ncclGetUniqueId failed";
+    return FZ_ERR_CUDA;
+  }
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, sizeof(id));
+  return FZ_OK;
+}
+int fz_comm_init(fz_engine* e, const void* unique_id128) { FZ_GUARD(e, e->impl->comm_init(unique_id128)) }
+
+int fz_group_comm_init(fz_engine** engines, int n) {
+  unsigned char id[128];
+  const int rc = fz_comm_unique_id(id);
+  if (rc != FZ_OK) return rc;
+  return for_each_engine(engines, n, [&](fz_engine* e) { return fz_comm_init(e, id); });
+}
+int fz_group_iterate(fz_engine** engines, int n, int algo, int n_iters) {
+  return for_each_engine(engines, n, [&](fz_engine* e) {
+    const int rc = fz_iterate(e, algo, n_iters, nullptr);
+    if (rc != FZ_OK) return rc;
+    DeviceGuard guard(e->impl->device);
+    return cudaStreamSynchronize(nullptr) == cudaSuccess ? (int)FZ_OK : (int)FZ_ERR_CUDA;
+  });
+}
+int fz_group_objective(fz_engine** engines, int n, double* per_relation, double* total) {
+  // every rank computes its share and takes part in the all-reduce; rank 0's (identical) result is returned
+  return for_each_engine(engines, n, [&](fz_engine* e) {
+    const bool first = (e == engines[0]);
+    return fz_objective(e, first ? per_relation : nullptr, first ? total : nullptr, nullptr);
+  });
+}
+
 int fz_add_type(fz_engine* e, int64_t n, int k) {
   if (!e || !e->impl) return FZ_ERR_INVALID;
+  DeviceGuard guard(e->impl->device);
   try {
     return e->impl->add_type(n, k);
   } catch (const fz::FzError& err_) {
     e->impl->err = err_.msg;
     return err_.status;
+  } catch (const std::exception& ex_) {
+    e->impl->err = ex_.what();
+    return FZ_ERR_INVALID;
+  } catch (...) {
+    e->impl->err = "unknown C++ exception";
+    return FZ_ERR_INVALID;
   }
 }
 
 int fz_add_relation(fz_engine* e, int ti, int tj, const void* data, int64_t ld, int src, int mem, int storage, int borrow,
                     const uint8_t* mask, int64_t mask_ld, int mask_mem) {
   if (!e || !e->impl) return FZ_ERR_INVALID;
+  DeviceGuard guard(e->impl->device);
   try {
     return e->impl->add_relation(ti, tj, data, ld, src, mem, storage, borrow, mask, mask_ld, mask_mem);
   } catch (const fz::FzError& err_) {
     e->impl->err = err_.msg;
     return err_.status;
+  } catch (const std::exception& ex_) {
+    e->impl->err = ex_.what();
+    return FZ_ERR_INVALID;
+  } catch (...) {
+    e->impl->err = "unknown C++ exception";
+    return FZ_ERR_INVALID;
   }
 }
 
@@ -1749,6 +1980,9 @@ int fz_profile_read(fz_engine* e, int64_t* launches, double* total_ms, double* s
 int fz_fill_uniform(void* dst, int dtype, int64_t ld, int64_t rows, int64_t cols, int64_t row0, uint64_t seed, void* stream) {
   if (!dst || rows < 0 || cols < 0 || ld < cols) return FZ_ERR_INVALID;
   if (rows * cols == 0) return FZ_OK;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, dst) != cudaSuccess || attr.type != cudaMemoryTypeDevice) return FZ_ERR_INVALID;
+  DeviceGuard guard(attr.device);                 // launch where the buffer lives, whatever the caller's current device
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = fz::nblk(rows * cols, 256);
   if (dtype == FZ_BF16) fz::fill_hashed_uniform<__nv_bfloat16><<<g, 256, 0, st>>>((__nv_bfloat16*)dst, ld, rows, cols, row0, seed);
@@ -1761,6 +1995,9 @@ int fz_fill_uniform(void* dst, int dtype, int64_t ld, int64_t rows, int64_t cols
 int fz_fill_unknown(void* data, int dtype, int64_t ld, int64_t rows, int64_t cols, int mode, double value, void* stream) {
   if (!data || rows < 0 || cols < 0 || ld < cols || mode < 0 || mode > 3) return FZ_ERR_INVALID;
   if (rows * cols == 0) return FZ_OK;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, data) != cudaSuccess || attr.type != cudaMemoryTypeDevice) return FZ_ERR_INVALID;
+  DeviceGuard guard(attr.device);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FZ_BF16) return fill_unknown_impl<__nv_bfloat16>((__nv_bfloat16*)data, ld, rows, cols, mode, value, st);
   if (dtype == FZ_F32) return fill_unknown_impl<float>((float*)data, ld, rows, cols, mode, value, st);

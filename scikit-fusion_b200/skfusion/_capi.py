@@ -21,7 +21,8 @@ FZ_TERMS_AUTO, FZ_TERMS_CENTRED1 = 0, -1
 
 # every symbol include/fz_fusion.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "fz_create", "fz_destroy", "fz_last_error", "fz_version", "fz_launch_count", "fz_set_shard", "fz_add_type",
+    "fz_create", "fz_destroy", "fz_last_error", "fz_version", "fz_launch_count", "fz_set_shard", "fz_comm_unique_id", "fz_comm_init", "fz_group_comm_init", "fz_group_iterate",
+    "fz_group_objective", "fz_add_type",
     "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_operand_stats", "fz_finalize", "fz_iterate",
     "fz_phase_products", "fz_phase_update", "fz_phase_products_begin", "fz_phase_product_relation", "fz_phase_products_end", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
     "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete",
@@ -80,6 +81,11 @@ def lib():
         "fz_version": (i32, []),
         "fz_launch_count": (i64, [vp]),
         "fz_set_shard": (i32, [vp, i32, i32]),
+        "fz_comm_unique_id": (i32, [vp]),
+        "fz_comm_init": (i32, [vp, vp]),
+        "fz_group_comm_init": (i32, [c_void_pp, i32]),
+        "fz_group_iterate": (i32, [c_void_pp, i32, i32, i32]),
+        "fz_group_objective": (i32, [c_void_pp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
         "fz_add_type": (i32, [vp, i64, i32]),
         "fz_add_relation": (i32, [vp, i32, i32, vp, i64, i32, i32, i32, i32, vp, i64, i32]),
         "fz_set_factor": (i32, [vp, i32, vp, i64, i32, i32]),
@@ -133,6 +139,47 @@ def dtype_code(name):
         return _DTYPE_NAMES[str(name).replace("torch.", "")]
     except KeyError:
         raise ValueError("unknown dtype %r (float64 | float32 | bfloat16)" % (name,))
+
+
+def comm_unique_id():
+    """128-byte NCCL id made by one rank and handed to every rank's Engine.comm_init."""
+    L = lib()
+    buf = ctypes.create_string_buffer(128)
+    rc = L.fz_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p))
+    if rc < 0:
+        raise EngineError("engine error %d: %s" % (rc, L.fz_last_error(None).decode()))
+    return buf.raw
+
+
+class EngineGroup(object):
+    """The handles of one shard group driven from ONE process (rank i = engines[i], each on its own GPU): the group
+    calls run one host thread per handle inside the library (include/fz_fusion.h: fz_group_*)."""
+
+    def __init__(self, engines):
+        self.engines = list(engines)
+        self._L = lib()
+        self._arr = (ctypes.c_void_p * len(self.engines))(*[e._h.value for e in self.engines])
+
+    def _ck(self, rc):
+        if rc < 0:
+            msgs = [self._L.fz_last_error(e._h).decode() for e in self.engines]
+            raise EngineError("engine group error %d: %s" % (rc, " | ".join(m for m in msgs if m) or "?"))
+
+    def comm_init(self):
+        self._ck(self._L.fz_group_comm_init(self._arr, len(self.engines)))
+
+    def iterate(self, algo, n_iters):
+        self._ck(self._L.fz_group_iterate(self._arr, len(self.engines), algo, int(n_iters)))
+
+    def objective(self, n_relations):
+        per = (ctypes.c_double * max(1, n_relations))()
+        tot = ctypes.c_double()
+        self._ck(self._L.fz_group_objective(self._arr, len(self.engines), per, ctypes.byref(tot)))
+        return tot.value, list(per)[:n_relations]
+
+    def close(self):
+        for e in self.engines:
+            e.close()
 
 
 def fill_uniform(tensor, seed, row0=0, stream=0):
@@ -223,6 +270,12 @@ class Engine(object):
         self._ck(self._L.fz_set_shard(self._h, world, rank))
         self.world, self.rank = int(world), int(rank)
 
+    def comm_init(self, unique_id):
+        """Join the shard group's NCCL communicator (every rank, same 128-byte id, concurrently); fz_iterate and
+        fz_objective then run the collectives inside the library."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self._L.fz_comm_init(self._h, ctypes.cast(buf, ctypes.c_void_p)))
+
     def _local_rows(self, t):
         n = self.type_shape[t][0]
         m = (n + self.world - 1) // self.world
@@ -243,10 +296,12 @@ class Engine(object):
             raise ValueError("relation matrix has shape %r but its object types imply %r" % (tuple(data.shape), want))
         if mask is not None and tuple(int(d) for d in mask.shape) != want:
             raise ValueError("mask has shape %r but the relation is %r" % (tuple(mask.shape), want))
+        if not hasattr(data, "data_ptr") and np.asarray(data).dtype in (np.dtype(np.bool_), np.dtype(np.uint8)):
+            data = np.asarray(data, dtype=np.float64)   # binary relations are data, not masks (numpy promotes them upstream too)
+        elif hasattr(data, "data_ptr") and str(data.dtype) in ("torch.uint8", "torch.bool"):
+            data = data.double()
         keep, ptr, ld, code, mem = _describe(data)
         st = code if storage is None else dtype_code(storage)
-        if st == FZ_U8:
-            raise ValueError("relation data cannot be uint8")
         mkeep, mptr, mld, mmem = None, None, 0, FZ_HOST
         if mask is not None:
             if not _is_torch_cuda(mask):

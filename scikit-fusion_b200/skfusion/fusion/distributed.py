@@ -9,8 +9,12 @@ R_ij lives as the row block of type i's local rows.  One iteration is
     update     (local)  k x k chain (replicated) + multiplicative update of the local rows
     all-gather          the updated factors
 
-The same loop drives any ``shard`` object with the five methods below: the CUDA engine in sharded mode
-(``CudaShard``) in production, a numpy stand-in in the gloo CPU tests of the host logic.
+In production the collectives run INSIDE the library (``attach_comm``: NCCL on the engine's own stream, the
+reduce-scatter of relation r under the products of relation r+1, the Gram all-reduce and the pseudo-inverses under
+the first products, the all-gather of type t under the update of type t+1) and the whole loop is one
+``engine.iterate`` call.  ``run_iterations`` is the same loop spelled out on the host with torch.distributed
+collectives between the engine's phase calls: it drives any ``shard`` object with the five methods below -- the
+CUDA engine (``CudaShard``) or a numpy stand-in in the gloo CPU tests of the host logic.
 Transform and restarts do not shard: rows / runs are independent, so they run as replicas.
 """
 from .. import _capi
@@ -159,26 +163,47 @@ def build_sharded_engine(R_local, sizes, ranks, obj_types, G0, world, rank, devi
     eng.set_shard(world, rank)
     tid = {t: eng.add_type(sizes[t], int(ranks[t])) for t in obj_types}
     rel_ids = {}
+    storage = opts.get("storage")
+    want = _capi.FZ_BF16 if (storage and _capi.dtype_code(storage) == _capi.FZ_BF16) else eng.compute
     for key, mats in R_local.items():
         rel_ids[key] = []
         for mat in mats:
-            borrow = _capi._is_torch_cuda(mat)
-            rel_ids[key].append(eng.add_relation(tid[key[0]], tid[key[1]], mat, storage=opts.get("storage"), borrow=borrow))
+            # device tensors already in the dtype the engine keeps are used in place; anything else is copied / converted
+            borrow = (_capi._is_torch_cuda(mat) and _capi.dtype_code(str(mat.dtype)) == want and mat.stride(1) == 1 and
+                      (want != _capi.FZ_BF16 or (mat.stride(0) % 8 == 0 and mat.data_ptr() % 16 == 0)))
+            rel_ids[key].append(eng.add_relation(tid[key[0]], tid[key[1]], mat, storage=storage, borrow=borrow))
     for t in obj_types:
         eng.set_factor(tid[t], G0[t, t])
     eng.finalize()
     return eng, tid, rel_ids
 
 
-def dfmf_sharded(R_local, obj_types, sizes, obj_type2rank, G0, max_iter, dist, device=0, group=None, **opts):
-    """DFMF over torch.distributed: every rank passes the row blocks it owns (``local_rows``) and the
-    same full initial factors; returns the full factors and the (replicated) backbones on every rank."""
+def attach_comm(eng, dist, group=None):
+    """Give the engine its own NCCL communicator over the ranks of ``dist`` (rank 0 makes the id, torch.distributed
+    only carries the 128 bytes).  Afterwards ``eng.iterate`` runs the sharded loop, collectives included."""
+    box = [_capi.comm_unique_id() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    eng.comm_init(box[0])
+
+
+def dfmf_sharded(R_local, obj_types, sizes, obj_type2rank, G0, max_iter, dist, device=0, group=None, collectives="library",
+                 **opts):
+    """DFMF over the ranks of torch.distributed: every rank passes the row blocks it owns (``local_rows``) and the
+    same full initial factors; returns the full factors and the (replicated) backbones on every rank.
+    collectives = "library" (NCCL inside the engine; needs the nccl backend) or "host" (torch.distributed calls between
+    the engine's phases: the spelled-out loop, also what the gloo tests drive)."""
     coll = Collectives(dist, group)
+    opts.pop("n_gpus", None)
     eng, tid, rel_ids = build_sharded_engine(R_local, sizes, obj_type2rank, obj_types, G0, coll.world, coll.rank, device, opts)
     try:
-        shard = CudaShard(eng, device, sum(len(v) for v in rel_ids.values()), len(obj_types))
-        shard.world, shard.rank = coll.world, coll.rank
-        run_iterations(shard, coll, max_iter)
+        if collectives == "library" and coll.native_rs and coll.world > 1:
+            import torch
+            attach_comm(eng, dist, group)
+            eng.iterate(_capi.FZ_DFMF, max_iter, torch.cuda.current_stream(device).cuda_stream)
+        else:
+            shard = CudaShard(eng, device, sum(len(v) for v in rel_ids.values()), len(obj_types))
+            shard.world, shard.rank = coll.world, coll.rank
+            run_iterations(shard, coll, max_iter)
         G = {(t, t): eng.get_factor(tid[t]) for t in obj_types}
         S = {key: [eng.get_backbone(i) for i in ids] for key, ids in rel_ids.items()}
         return G, S

@@ -21,7 +21,7 @@ from .graph import DataFusionError
 
 __all__ = ['FusionBase', 'FusionFit', 'FusionTransform', 'DataFusionError', 'Dfmf', 'Dfmc', 'DfmfTransform']
 
-_ENGINE_KEYS = ("device", "dtype", "storage", "split_terms", "device_init")
+_ENGINE_KEYS = ("device", "dtype", "storage", "split_terms", "device_init", "n_gpus")
 
 
 class FusionBase(object):

@@ -17,6 +17,10 @@ Defaults can be changed process-wide (``engine_options.update(dtype='float64')``
                (default: on the GPU when a relation is already device-resident or the graph has more than
                AUTO_FP64_MAX_ENTRIES entries, otherwise with numpy on the host exactly like the reference), True, False.
                The RandomState is consumed identically either way (initializers.py).
+  n_gpus       GPUs of this box a Dfmf fit is spread over (default 1): the rows of every object type are split contiguously
+               over devices device .. device + n_gpus - 1, driven from this one process (one host thread per GPU inside the
+               library, NCCL over NVLink for the three exchanges).  Dfmc and DfmfTransform stay on
+               one GPU (their rows / runs are independent: run replicas).
 """
 import os
 
@@ -30,6 +34,7 @@ engine_options = {
     "storage": os.environ.get("SKFUSION_B200_STORAGE") or None,
     "split_terms": _terms(os.environ.get("SKFUSION_B200_SPLIT_TERMS", "2")),
     "device_init": {"1": True, "0": False}.get(os.environ.get("SKFUSION_B200_DEVICE_INIT", ""), "auto"),
+    "n_gpus": int(os.environ.get("SKFUSION_B200_N_GPUS", "1")),
 }
 
 
@@ -40,6 +45,8 @@ def resolve(n_entries=None, **overrides):
     """Effective engine options; ``n_entries`` (total relation + constraint entries) settles dtype='auto'."""
     opts = dict(engine_options)
     for key, val in overrides.items():
+        if key not in engine_options:
+            raise TypeError("unknown engine option %r (known: %s)" % (key, ", ".join(sorted(engine_options))))
         if val is not None:
             opts[key] = val
     if opts["dtype"] == "auto":

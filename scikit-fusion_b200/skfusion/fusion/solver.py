@@ -6,7 +6,8 @@ consumption, initializers.py), early-stopping bookkeeping, logging, the user cal
 inside ``for iter in range(max_iter)`` runs in the CUDA engine (include/fz_fusion.h); without a
 callback / error tracking the whole loop is ONE C call with no host round trips.
 
-Engine-only keyword arguments (all optional, see options.py): device, dtype, storage, split_terms.
+Engine-only keyword arguments (all optional, see options.py): device, dtype, storage, split_terms, device_init, n_gpus
+(n_gpus > 1: the rows of every object type are sharded over that many GPUs of the box, driven from this process).
 Relation matrices may be numpy arrays (copied to the GPU) or torch CUDA tensors (used in place when
 their dtype equals the storage dtype).
 """
@@ -19,6 +20,19 @@ from .initializers import initialize, initialize_on_device
 from .options import resolve
 
 log = logging.getLogger("skfusion.fusion")
+
+# diagnostics of the most recent fit of this process (engine launches, which fused kernel ran how often, gate measurements)
+last_fit_info = {}
+
+
+def _record(engine, **extra):
+    last_fit_info.clear()
+    last_fit_info.update(extra)
+    try:
+        last_fit_info["launches"] = engine.launches
+        last_fit_info["operand_stats"] = engine.operand_stats()
+    except Exception:       # diagnostics must never fail a fit
+        pass
 
 
 def count_objects(obj_types, R):
@@ -41,12 +55,26 @@ def _configure_logging(verbose):
                         level=50 - verbose)
 
 
+def _device_of(R, Theta, opts):
+    """Device the handle lives on: where the caller's CUDA relations already are (they are used in place), else the
+    configured one.  Relations spread over several devices cannot be borrowed by one handle."""
+    found = set()
+    for block in (R, Theta or {}):
+        for mats in block.values():
+            for mat in mats:
+                if _capi._is_torch_cuda(mat):
+                    found.add(int(mat.device.index if mat.device.index is not None else 0))
+    if len(found) > 1:
+        raise ValueError("relation tensors live on different CUDA devices %s: move them to one device (or use n_gpus)" % sorted(found))
+    return found.pop() if found else int(opts["device"])
+
+
 class _Problem(object):
     """One engine handle plus the id maps between the reference's dict keys and engine ids."""
 
-    def __init__(self, opts):
+    def __init__(self, opts, device=None):
         self.opts = opts
-        self.engine = _capi.Engine(device=opts["device"], compute=opts["dtype"])
+        self.engine = _capi.Engine(device=opts["device"] if device is None else device, compute=opts["dtype"])
         if opts.get("split_terms") is not None:
             self.engine.set_split_terms(opts["split_terms"])
         self.type_id = {}
@@ -77,8 +105,13 @@ class _Problem(object):
     def _can_borrow(self, mat, storage, mask):
         if mask is not None or not _capi._is_torch_cuda(mat):
             return False
-        want = _capi.dtype_code(storage) if storage else self.engine.compute
-        return _capi.dtype_code(str(mat.dtype)) == want and (want != _capi.FZ_BF16 or mat.stride(0) % 8 == 0)
+        # the engine keeps a relation in bf16 only when asked to, otherwise in its compute dtype (fz_add_relation)
+        want = _capi.FZ_BF16 if (storage and _capi.dtype_code(storage) == _capi.FZ_BF16) else self.engine.compute
+        try:
+            have = _capi.dtype_code(str(mat.dtype))
+        except ValueError:
+            return False
+        return have == want and mat.stride(1) == 1 and (want != _capi.FZ_BF16 or (mat.stride(0) % 8 == 0 and mat.data_ptr() % 16 == 0))
 
     def factors(self):
         return {(t, t): self.engine.get_factor(self.type_id[t]) for t in self.type_order}
@@ -106,6 +139,9 @@ def _fit(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopp
          compute_err, callback, random_state, engine_kwargs):
     _configure_logging(verbose)
     opts = resolve(n_entries=_count_entries(R, Theta), **engine_kwargs)
+    if int(opts.get("n_gpus") or 1) > 1:
+        return _fit_sharded(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopping, stopping_system,
+                            compute_err, callback, random_state, opts)
     sizes = count_objects(obj_types, R)
     on_device = _init_on_device(opts, init_type, R, Theta)
     G0 = None
@@ -115,7 +151,7 @@ def _fit(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopp
     if stopping_system:
         compute_err = True
 
-    prob = _Problem(opts)
+    prob = _Problem(opts, _device_of(R, Theta, opts))
     try:
         prob.add_types(obj_types, sizes, obj_type2rank)
         prob.add_blocks(R, Theta, M)
@@ -168,7 +204,89 @@ def _fit(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopp
             G, S = prob.factors(), prob.backbones()
         return G, S
     finally:
+        _record(prob.engine, n_gpus=1)
         prob.close()
+
+
+def _row_block(mat, lo, hi, device):
+    """Rows [lo, hi) of a relation for the rank living on ``device``: a numpy view, or the tensor slice moved there."""
+    if _capi._is_torch_cuda(mat):
+        blk = mat[lo:hi]
+        return blk if int(mat.device.index or 0) == device else blk.to("cuda:%d" % device)
+    return mat[lo:hi]
+
+
+def _fit_sharded(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopping, stopping_system, compute_err,
+                 callback, random_state, opts):
+    """dfmf over n_gpus GPUs of this box from ONE process (reference entry: Dfmf.fuse -> dfmf(), dfmf.py:55-106): rank p's
+    handle lives on device p and holds the row blocks [lo_p, hi_p) of every relation; the handles form one shard group and the
+    library runs one host thread per handle with NCCL for the three exchanges (include/fz_fusion.h: fz_group_*).  Objective,
+    early stopping and the callback work as on one GPU; results are read from rank 0 (every rank holds the whole factors)."""
+    from .distributed import local_rows
+    if algo != _capi.FZ_DFMF:
+        raise ValueError("n_gpus > 1 is for Dfmf; Dfmc re-imputes whole relations every iteration and runs on one GPU")
+    world = int(opts["n_gpus"])
+    base = int(opts["device"])
+    sizes = count_objects(obj_types, R)
+    first = {key: _host_view(mats[0]) for key, mats in R.items()} if init_type != "random" else {}
+    G0 = initialize(obj_types, sizes, obj_type2rank, first, init_type, random_state)     # on the host: RNG-exact
+    if stopping_system:
+        compute_err = True
+    probs = []
+    try:
+        for p in range(world):
+            prob = _Problem(opts, base + p)
+            probs.append(prob)
+            prob.engine.set_shard(world, p)
+            prob.add_types(obj_types, sizes, obj_type2rank)
+            block = lambda blocks: {key: [_row_block(mat, *local_rows(sizes[key[0]], world, p), base + p) for mat in mats]
+                                    for key, mats in blocks.items()}
+            prob.add_blocks(block(R), block(Theta), None)
+            for t in obj_types:
+                prob.engine.set_factor(prob.type_id[t], G0[t, t])
+            prob.engine.finalize()
+        group = _capi.EngineGroup([prob.engine for prob in probs])
+        group.comm_init()
+        head = probs[0]
+        if not (stopping or compute_err or callback):
+            if max_iter > 0:
+                group.iterate(algo, max_iter)
+                return head.factors(), head.backbones()
+            return G0, None
+        err_target, err_system, history = (None, None), (None, None), []
+        G, S = G0, None
+        for it in range(max_iter):
+            if it > 1 and stopping and err_target[1] - err_target[0] < stopping[1]:
+                log.info("Early stopping: target matrix change < %5.4f" % stopping[1])
+                break
+            if it > 1 and stopping_system and err_system[1] - err_system[0] < stopping_system:
+                log.info("Early stopping: matrix system change < %5.4f" % stopping_system)
+                break
+            log.info("Factorization iteration: %d" % it)
+            group.iterate(algo, 1)
+            if stopping or compute_err:
+                total, per_rel = group.objective(head.n_relations())
+                if stopping:
+                    tkey, tl = _target_of(stopping)
+                    err_target = (per_rel[head.relation_index(tkey, tl)], err_target[0])
+                if compute_err:
+                    log.info("Error (objective function value): %5.4f" % total)
+                    history.append(total)
+                    if stopping_system:
+                        err_system = (total, err_system[0])
+            if callback:
+                G, S = head.factors(), head.backbones()
+                callback(G, S, it)
+        if compute_err and history:
+            log.info("Violations of optimization objective: %d/%d " % (int(np.sum(np.diff(history) > 0)), len(history)))
+        if max_iter > 0:
+            G, S = head.factors(), head.backbones()
+        return G, S
+    finally:
+        if probs:
+            _record(probs[0].engine, n_gpus=world)
+        for prob in probs:
+            prob.close()
 
 
 def _init_on_device(opts, init_type, R, Theta):
@@ -246,7 +364,7 @@ def transform(R_ij, Theta_i, target_obj_type, obj_type2rank, G, S, max_iter=10, 
         if max_iter <= 0:
             return G_i
 
-    prob = _Problem(opts)
+    prob = _Problem(opts, _device_of(R_ij, Theta_i, opts))
     try:
         involved = []
         for (ti, tj), mats in R_ij.items():
