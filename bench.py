@@ -276,19 +276,15 @@ def gpu_arm(args):
     G0 = {(t, t): rs.rand(n, RANK).astype(np.float32) for t in types}
     opts = dict(dtype="float32", storage="bfloat16", split_terms=args.split_terms)
     eng, tid, rel_ids = fzd.build_sharded_engine(R_local, sizes, ranks, types, G0, world, rank, local, opts)
-    shard = fzd.CudaShard(eng, local, len(PAIRS), N_TYPES)
-    shard.world, shard.rank = world, rank
-
-    class Solo(object):
-        world, rank = 1, 0
-    coll = fzd.Collectives(dist) if world > 1 else Solo()
+    if world > 1:
+        fzd.attach_comm(eng, dist)       # NCCL inside the library: the whole sharded iteration is one C call
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    fzd.run_iterations(shard, coll, args.warmup)
+    eng.iterate(_capi.FZ_DFMF, args.warmup, stream)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -298,7 +294,7 @@ def gpu_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    fzd.run_iterations(shard, coll, args.steps)
+    eng.iterate(_capi.FZ_DFMF, args.steps, stream)
     e1.record()
     if rank == 0:
         sampler.sample_instant_power()   # the host has only enqueued the steps: the GPU is in the middle of the timed region
@@ -371,9 +367,9 @@ def gpu_arm(args):
     Sf = {key: [eng.get_backbone(i) for i in ids] for key, ids in rel_ids.items()}
     check = _check_sums(Gf, Sf, args.warmup + args.steps)
     del Gf, Sf
+    operand = eng.operand_stats()
     e2e = None
     eng.close()                      # frees the engine's buffers and drops its references to the borrowed relations
-    del shard
     if not args.no_e2e:
         e2e = e2e_leg(args, torch, dist, fzd, _capi, R_local, G0, types, sizes, ranks, world, rank, local, dev, opts, n, lo, hi)
 
@@ -396,6 +392,9 @@ def gpu_arm(args):
                        "relation_bytes_total": 10 * n * n * 2,
                        "cache": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (10.0 * n * (hi - lo) * 2 / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "check": check, "parity": parity,
+            "operand_form": {"split_terms": args.split_terms, "single_term_iterations": operand["single"],
+                             "two_term_iterations": operand["two_term"], "gate_error_estimate": operand["err"],
+                             "gate_cond_estimate": operand["cond"]},
             "clocks": sampler.summary(),
         }
     if world > 1:
@@ -406,12 +405,13 @@ def gpu_arm(args):
 
 
 def e2e_leg(args, torch, dist, fzd, _capi, R_dev, G0, types, sizes, ranks, world, rank, local, dev, opts, n, lo, hi):
-    """K iterations through build_sharded_engine + run_iterations with HOST inputs: relation row blocks in
-    pinned host memory (bf16), factors as host float32; outputs read back to host numpy."""
+    """K iterations end to end through the public API with HOST inputs: relation row blocks in pinned host memory (bf16),
+    factors as host float32; outputs read back to host numpy.  One GPU: solver.dfmf (the reference's seam function);
+    several GPUs under torch.distributed.run: distributed.dfmf_sharded, its one-process-per-GPU form."""
     import psutil
+    from skfusion.fusion import solver
     need = 10.0 * (hi - lo) * n * 2
     avail = psutil.virtual_memory().available
-    note = None
     if need * 1.15 > avail / max(1, world if world > 1 else 1):
         return {"value": None, "unit": "it/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                 "note": "host RAM too small to stage the relations (%.0f GB needed, %.0f GB available)" % (need / 1e9, avail / 1e9)}
@@ -434,34 +434,41 @@ def e2e_leg(args, torch, dist, fzd, _capi, R_dev, G0, types, sizes, ranks, world
     gc.collect()
     torch.cuda.empty_cache()
 
-    class Solo(object):
-        world, rank = 1, 0
-    coll = fzd.Collectives(dist) if world > 1 else Solo()
+    class FixedInit(object):
+        """RandomState stand-in that hands the solver the bench's initial factors (host float32), in type order."""
+        def __init__(self):
+            self.order = iter(types)
+
+        def rand(self, rows, cols):
+            t = next(self.order)
+            return G0[t, t]
+
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    eng, tid, rel_ids = fzd.build_sharded_engine(host, sizes, ranks, types, G0, world, rank, local, opts)
-    shard = fzd.CudaShard(eng, local, len(rel_ids), len(types))
-    shard.world, shard.rank = world, rank
-    fzd.run_iterations(shard, coll, args.steps)
-    G = {t: eng.get_factor(tid[t]) for t in types}
-    S = {key: [eng.get_backbone(i) for i in ids] for key, ids in rel_ids.items()}
+    if world == 1:
+        G, S = solver.dfmf(host, {}, types, ranks, max_iter=args.steps, init_type="random", random_state=FixedInit(),
+                           device=local, **opts)
+    else:
+        G, S = fzd.dfmf_sharded(host, types, sizes, ranks, G0, args.steps, dist, device=local, **opts)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     dt = time.perf_counter() - t0
-    eng.close()
     if world > 1:
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
     h2d = need + sum(g.nbytes for g in G0.values())
-    d2h = sum(g.nbytes for g in G.values()) + sum(s.nbytes for v in S.values() for s in v)
+    d2h = sum(g.nbytes for g in G.values()) + sum(m.nbytes for v in S.values() for m in v)
     return {"value": round(args.steps / dt, 4), "unit": "it/s", "seconds_total": round(dt, 3),
             "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
-            "note": "one fit of %d iterations through the C ABI from pinned host buffers: upload of the relation row blocks "
-                    "(once per fit) + iterations + download of all factors and backbones, per rank" % args.steps}
+            "api": "skfusion.fusion.solver.dfmf" if world == 1 else "skfusion.fusion.distributed.dfmf_sharded",
+            "check": _check_sums(G, S, args.steps),
+            "note": "one fit of %d iterations through the public API from pinned host buffers: upload of the relation row blocks "
+                    "(once per fit, PCIe-bound: %.1f GB per GPU) + iterations + download of all factors and backbones, per rank" % (
+                        args.steps, need / 1e9)}
 
 
 def small_workload(args):

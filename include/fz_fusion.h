@@ -133,8 +133,15 @@ int fz_get_backbone(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype,
 /* Frobenius residuals ||R - G_i S G_j^T||_F per relation (un-squared, _dfmf.py:306-319) and their sum,
  * with the current factors and the backbones of the last iteration.  per_relation may be NULL. */
 int fz_objective(fz_engine* e, double* per_relation, double* total, void* stream);
-/* completed relation G_i S_ij G_j^T (base.py:119-146) into a caller buffer */
+/* completed relation G_i S_ij G_j^T (skfusion/fusion/base/base.py:119-146) into a caller buffer (n_i x n_j) */
 int fz_complete(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int mem, void* stream);
+/* G_ti M G_tj^T for a caller-given k_ti x k_tj matrix M (host or device): the chained profiles of the reference's examples,
+ * M = S_ab S_bc ... along a path of the fusion graph (base.py:69-96, examples/dicty_chaining.py:40-53), or a completion with
+ * any backbone.  fp32 engine with ranks <= 64: an output-bound tcgen05 product written by TMA stores (a device fp32
+ * destination with ld % 4 == 0 is written in place); otherwise an exact CUDA-core kernel.  Needs the two factors only: a
+ * handle with types, factors and no relations is enough. */
+int fz_profile_product(fz_engine* e, int ti, int tj, const void* M, int64_t ldm, int m_dtype, int m_mem, void* dst, int64_t ld,
+                       int dst_dtype, int mem, void* stream);
 
 /* ---- factor initialisation on the device ------------------------------------------------------
  * Reference: initialize() / _random_c / _random_vcol, skfusion/fusion/decomposition/_init.py:6-61.  The host keeps the

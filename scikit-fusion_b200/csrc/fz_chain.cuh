@@ -63,7 +63,8 @@ struct PinvJob {
   double* P;               // k x k output
   double* work;            // 3 * k * k doubles
   int* info;               // [0] = 0 Cholesky, 1 Jacobi ; [1] = numerical rank
-  double* cond;            // [1] estimate of cond_2(gram): (max L_ii / min L_ii)^2 (Cholesky, a lower bound) or
+  double* cond;            // [1] estimate of cond_2(gram): |gram|_F |P|_F / sqrt(k) (Cholesky path; between cond_2 / sqrt(k) and
+                           //     sqrt(k) cond_2, ~cond_2 for the usual one-dominant-direction Gram matrices) or
                            //     sigma_max / sigma_min over the kept singular values (Jacobi; 1e300 when rank-deficient)
   int k;
 };
@@ -130,7 +131,6 @@ pinv_spd(const PinvJob* __restrict__ jobs) {
       double lo = L[0], hi = L[0];
       for (int i = 1; i < k; ++i) { lo = fmin(lo, L[(long long)i * k + i]); hi = fmax(hi, L[(long long)i * k + i]); }
       const double c = (hi / lo) * (hi / lo);
-      if (job.cond) job.cond[0] = c;
       if (c * (double)k * 2.220446049250313e-16 > 1.0) s_fail = 1;
     }
     __syncthreads();
@@ -154,6 +154,24 @@ pinv_spd(const PinvJob* __restrict__ jobs) {
       job.P[o] = s;
     }
     if (tid == 0) { job.info[0] = 0; job.info[1] = k; }
+    if (job.cond != nullptr) {
+      // |gram|_F |P|_F / sqrt(k), summed by warp 0 in a fixed order (the estimate feeds a decision: keep it reproducible)
+      __syncthreads();
+      if (tid < 32) {
+        double sg = 0.0, sp = 0.0;
+        for (int o = tid; o < k * k; o += 32) {
+          const double g = job.gram[o], q = job.P[o];
+          sg += g * g;
+          sp += q * q;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          sg += __shfl_xor_sync(0xffffffffu, sg, off);
+          sp += __shfl_xor_sync(0xffffffffu, sp, off);
+        }
+        if (tid == 0) job.cond[0] = sqrt(sg * sp / (double)k);
+      }
+    }
     return;
   }
 

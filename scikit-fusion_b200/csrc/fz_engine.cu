@@ -30,6 +30,7 @@
 #include "umma_fused.cuh"
 #include "umma_fused1.cuh"
 #include "umma_fused_t.cuh"
+#include "umma_outer.cuh"
 #include "umma_skinny.cuh"
 
 namespace fz {
@@ -155,6 +156,8 @@ class EngineBase {
   virtual void get_backbone(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) = 0;
   virtual void objective(double* per_rel, double* total, cudaStream_t st) = 0;
   virtual void complete(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) = 0;
+  virtual void profile_product(int ti, int tj, const void* S, int64_t lds, int sd, int smem, void* dst, int64_t ld, int dd, int mem,
+                               cudaStream_t st) = 0;
   virtual void init_fill(int t, double value, cudaStream_t st) = 0;
   virtual void relation_norms(int rel, int axis, double* dst_host, cudaStream_t st) = 0;
   virtual void init_add_sampled_means(int t, int rel, const int32_t* idx_host, int p_c, cudaStream_t st) = 0;
@@ -1003,25 +1006,52 @@ class Engine : public EngineBase {
     if (total) *total = sum;
   }
 
+  // completed relation G_i S_ij G_j^T (base.py:119-146)
   void complete(int rel, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) override {
     need_final();
     RelRec& r = relation(rel);
     if (r.theta) FZ_THROW(FZ_ERR_INVALID, "constraint matrices cannot be completed");
-    TypeRec& Ti = *types_[r.ti];
-    TypeRec& Tj = *types_[r.tj];
-    ensure_T1(r);
-    gemm(cur(Ti), Ti.k, r.W4.template as<T>(), Tj.k, r.T1.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, Ti.k, false, st);
-    DevBuf out;
-    out.alloc((size_t)std::max<int64_t>(1, r.rows_loc) * r.cols * sizeof(T), false);
-    dim3 g(nblk(r.cols, 32), nblk(r.rows_loc, 32));
-    recon_err<T, T><<<g, 256, 0, st>>>(nullptr, 0, r.T1.template as<T>(), Tj.k, cur(Tj), Tj.k, r.rows_loc, r.cols, Tj.k, nullptr,
-                                       out.template as<T>(), r.cols);
+    wait_gathers(st);
+    product_GSG(r.ti, r.tj, r.S.template as<double>(), dst, ld, dd, mem, st);
+  }
+  // G_i M G_j^T for a caller-given k_i x k_j matrix M: chained profiles G_i (S_ab S_bc ...) G_j^T
+  // (examples/dicty_chaining.py:40-53) and completions with any backbone
+  void profile_product(int ti, int tj, const void* S, int64_t lds, int sd, int smem, void* dst, int64_t ld, int dd, int mem,
+                       cudaStream_t st) override {
+    need_final();
+    if (ti < 0 || tj < 0 || ti >= (int)types_.size() || tj >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id");
+    if (S == nullptr || dst == nullptr) FZ_THROW(FZ_ERR_INVALID, "null matrix");
+    check_factors();
+    wait_gathers(st);
+    const int ki = types_[ti]->k, kj = types_[tj]->k;
+    DevBuf Sd;
+    Sd.alloc((size_t)ki * kj * 8, false);
+    copy_in(S, lds, sd, smem, Sd.p, kj, FZ_F64, ki, kj, st);
+    product_GSG(ti, tj, Sd.template as<double>(), dst, ld, dd, mem, st);
+    CUDA_OK(cudaStreamSynchronize(st));     // Sd dies here
+  }
+
+ private:
+  // out (n_i x n_j) = G_i S G_j^T with S a device fp64 k_i x k_j matrix.  fp32 engine, ranks <= 64, unsharded: tensor cores
+  // (umma_outer.cuh: two bf16 terms per operand, output-bound).  Otherwise the exact CUDA-core tile kernel.
+  void product_GSG(int ti, int tj, const double* S_dev, void* dst, int64_t ld, int dd, int mem, cudaStream_t st);
+  void product_GSG_simt(TypeRec& Ti, TypeRec& Tj, const T* W, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) {
+    DevBuf t1, out;
+    t1.alloc((size_t)std::max<int64_t>(1, Ti.n) * Tj.k * sizeof(T), false);
+    gemm(cur(Ti), Ti.k, W, Tj.k, t1.template as<T>(), Tj.k, (int)Ti.n, Tj.k, Ti.k, false, st);
+    const bool direct = (mem == FZ_DEVICE && dd == kDT);
+    if (!direct) out.alloc((size_t)std::max<int64_t>(1, Ti.n) * Tj.n * sizeof(T), false);
+    T* C = direct ? (T*)dst : out.template as<T>();
+    const int64_t ldc = direct ? ld : Tj.n;
+    dim3 g(nblk(Tj.n, 32), nblk(Ti.n, 32));
+    recon_err<T, T><<<g, 256, 0, st>>>(nullptr, 0, t1.template as<T>(), Tj.k, cur(Tj), Tj.k, Ti.n, Tj.n, Tj.k, nullptr, C, ldc);
     ++launches;
     CUDA_OK(cudaGetLastError());
-    copy_out(out.p, r.cols, kDT, dst, ld, dd, mem, r.rows_loc, r.cols, st);
+    if (!direct) copy_out(out.p, Tj.n, kDT, dst, ld, dd, mem, Ti.n, Tj.n, st);
     CUDA_OK(cudaStreamSynchronize(st));
   }
 
+ public:
   // ---------------------------------------------------------------------------------------------
   // Factor initialisation on the device (reference _init.py:20-61).  The host draws the
   // column samples with numpy's RandomState (bit-exact RNG consumption); the O(k n^2) part -- the means over the sampled
@@ -1605,6 +1635,60 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
 }
 template <>
 bool Engine<double>::product_AB_fused(RelRec&, cudaStream_t) { return false; }
+
+// S (fp64) -> the compute dtype, row-major k_i x k_j
+template <class T>
+__global__ void cast_small(const double* __restrict__ S, T* __restrict__ W, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) W[i] = (T)S[i];
+}
+template <>
+void Engine<double>::product_GSG(int ti, int tj, const double* S_dev, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) {
+  product_GSG_simt(*types_[ti], *types_[tj], S_dev, dst, ld, dd, mem, st);
+}
+template <>
+void Engine<float>::product_GSG(int ti, int tj, const double* S_dev, void* dst, int64_t ld, int dd, int mem, cudaStream_t st) {
+  TypeRec& Ti = *types_[ti];
+  TypeRec& Tj = *types_[tj];
+  DevBuf W;
+  W.alloc((size_t)Ti.k * Tj.k * sizeof(float), false);
+  cast_small<float><<<nblk((long long)Ti.k * Tj.k, 256), 256, 0, st>>>(S_dev, W.template as<float>(), Ti.k * Tj.k);
+  ++launches;
+  const bool tensor = world_ == 1 && Ti.k <= kKp && Tj.k <= kKp && Ti.n >= 128 && Tj.n >= 128 && getenv("FZ_NO_OUTER") == nullptr;
+  if (!tensor) {
+    product_GSG_simt(Ti, Tj, W.template as<float>(), dst, ld, dd, mem, st);
+    return;
+  }
+  // T1 = G_i S (n_i x k_j), then the operand forms of the output-bound product T1 G_j^T
+  DevBuf t1, x3, y3, out;
+  t1.alloc((size_t)Ti.n * Tj.k * sizeof(float), false);
+  gemm(cur(Ti), Ti.k, W.template as<float>(), Tj.k, t1.template as<float>(), Tj.k, (int)Ti.n, Tj.k, Ti.k, false, st);
+  x3.alloc((size_t)Ti.n * kOuK * 2, false);
+  y3.alloc((size_t)Tj.n * kOuK * 2, false);
+  outer_operand<float><<<nblk(Ti.n * 64, 256), 256, 0, st>>>(t1.template as<float>(), Tj.k, x3.template as<__nv_bfloat16>(), Ti.n, Ti.n, Tj.k, 0);
+  outer_operand<float><<<nblk(Tj.n * 64, 256), 256, 0, st>>>(cur(Tj), Tj.k, y3.template as<__nv_bfloat16>(), Tj.n, Tj.n, Tj.k, 1);
+  launches += 2;
+  const bool direct = mem == FZ_DEVICE && dd == FZ_F32 && (ld % 4) == 0 && ((uintptr_t)dst & 15) == 0;
+  if (!direct) out.alloc((size_t)Ti.n * (size_t)(((Tj.n + 3) / 4) * 4) * sizeof(float), false);
+  float* C = direct ? (float*)dst : out.template as<float>();
+  const int64_t ldc = direct ? ld : ((Tj.n + 3) / 4) * 4;
+  CUtensorMap tx, ty, tc;
+  std::string e;
+  if (!make_tmap_bf16_2d(&tx, x3.p, (uint64_t)Ti.n, kOuK, kOuK, 64, 128, &e) || !make_tmap_bf16_2d(&ty, y3.p, (uint64_t)Tj.n, kOuK, kOuK, 64, 128, &e) ||
+      !make_tmap_f32_2d(&tc, C, (uint64_t)Ti.n, (uint64_t)Tj.n, (uint64_t)ldc, 32, 32, &e))
+    FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+  OuterParams q;
+  q.M = (int)Ti.n;
+  q.N = (int)Tj.n;
+  const long long units = (long long)((Ti.n + kOuTile - 1) / kOuTile) * ((Tj.n + kOuTile - 1) / kOuTile);
+  const unsigned ctas = (unsigned)std::max<long long>(1, std::min<long long>(sm_count_, units));
+  cudaFuncSetAttribute(umma_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOuSmemBytes);
+  umma_outer_kernel<<<ctas, kOuThreads, kOuSmemBytes, st>>>(tx, ty, tc, q);
+  ++launches;
+  CUDA_OK(cudaGetLastError());
+  if (!direct) copy_out(out.p, ldc, FZ_F32, dst, ld, dd, mem, Ti.n, Tj.n, st);
+  CUDA_OK(cudaStreamSynchronize(st));     // the operand buffers die here
+}
 template <>
 void Engine<float>::corr_M(RelRec& r, cudaStream_t st) {
   TypeRec& Ti = *types_[r.ti];
@@ -1934,6 +2018,10 @@ int fz_objective(fz_engine* e, double* per_relation, double* total, void* stream
 }
 int fz_complete(fz_engine* e, int rel, void* dst, int64_t ld, int dst_dtype, int mem, void* stream) {
   FZ_GUARD(e, e->impl->complete(rel, dst, ld, dst_dtype, mem, (cudaStream_t)stream))
+}
+int fz_profile_product(fz_engine* e, int ti, int tj, const void* S, int64_t lds, int s_dtype, int s_mem, void* dst, int64_t ld,
+                       int dst_dtype, int mem, void* stream) {
+  FZ_GUARD(e, e->impl->profile_product(ti, tj, S, lds, s_dtype, s_mem, dst, ld, dst_dtype, mem, (cudaStream_t)stream))
 }
 
 int fz_init_fill(fz_engine* e, int t, double value, void* stream) {

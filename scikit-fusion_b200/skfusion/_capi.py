@@ -25,7 +25,7 @@ SYMBOLS = [
     "fz_group_objective", "fz_add_type",
     "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_operand_stats", "fz_finalize", "fz_iterate",
     "fz_phase_products", "fz_phase_update", "fz_phase_products_begin", "fz_phase_product_relation", "fz_phase_products_end", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
-    "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete",
+    "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete", "fz_profile_product",
     "fz_fill_uniform", "fz_profile", "fz_profile_read",
     "fz_init_fill", "fz_relation_norms", "fz_init_add_sampled_means", "fz_init_end", "fz_fill_unknown",
 ]
@@ -108,6 +108,7 @@ def lib():
         "fz_get_backbone": (i32, [vp, i32, vp, i64, i32, i32, vp]),
         "fz_objective": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]),
         "fz_complete": (i32, [vp, i32, vp, i64, i32, i32, vp]),
+        "fz_profile_product": (i32, [vp, i32, i32, vp, i64, i32, i32, vp, i64, i32, i32, vp]),
         "fz_fill_uniform": (i32, [vp, i32, i64, i64, i64, i64, ctypes.c_uint64, vp]),
         "fz_init_fill": (i32, [vp, i32, ctypes.c_double, vp]),
         "fz_relation_norms": (i32, [vp, i32, i32, ctypes.POINTER(ctypes.c_double), vp]),
@@ -417,6 +418,25 @@ class Engine(object):
         out = np.empty((ni, nj), dtype=np.float64)
         self._ck(self._L.fz_complete(self._h, rel, ctypes.c_void_p(out.ctypes.data), nj, FZ_F64, FZ_HOST, ctypes.c_void_p(stream)))
         return out
+
+    def profile_product(self, ti, tj, M, out=None, stream=0):
+        """G_ti M G_tj^T (n_ti x n_tj): float64 numpy, or written into ``out`` (a 2-D torch CUDA tensor, float32 / float64)."""
+        M = np.ascontiguousarray(np.asarray(M, dtype=np.float64))
+        want = (self.type_shape[ti][1], self.type_shape[tj][1])
+        if M.shape != want:
+            raise ValueError("middle matrix has shape %r, expected %r" % (M.shape, want))
+        ni, nj = self.type_shape[ti][0], self.type_shape[tj][0]
+        if out is None:
+            res = np.empty((ni, nj), dtype=np.float64)
+            ptr, ld, code, mem = ctypes.c_void_p(res.ctypes.data), nj, FZ_F64, FZ_HOST
+        else:
+            if tuple(int(d) for d in out.shape) != (ni, nj):
+                raise ValueError("output has shape %r, expected %r" % (tuple(out.shape), (ni, nj)))
+            res = out
+            _keep, ptr, ld, code, mem = _describe(out)
+        self._ck(self._L.fz_profile_product(self._h, int(ti), int(tj), ctypes.c_void_p(M.ctypes.data), M.shape[1], FZ_F64, FZ_HOST,
+                                            ptr, ld, code, mem, ctypes.c_void_p(stream)))
+        return res
 
     # ---- factor initialisation on the device (_init.py:20-61; the RNG stays on the host)
     def init_fill(self, t, value, stream=0):

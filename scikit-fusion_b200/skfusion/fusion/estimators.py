@@ -8,14 +8,15 @@ transform, which run on the GPU.  Differences, all deliberate:
   * ``n_jobs`` is accepted and ignored: restarts run one after another on the device, sharing one
     RandomState exactly like the reference does for n_jobs=1 (results there change with n_jobs,
     SURVEY.md F3).
-  * extra keywords device / dtype / storage / split_terms select the engine configuration.
+  * extra keywords device / dtype / storage / split_terms / device_init / n_gpus select the engine configuration (options.py).
+  * ``complete`` and the new ``chain_profile`` run their n_row x n_col product on the GPU once it is large (device_ops.py).
 """
 from collections import defaultdict
 from itertools import product
 
 import numpy as np
 
-from . import solver
+from . import device_ops, solver
 from .. import _capi
 from .graph import DataFusionError
 
@@ -78,6 +79,22 @@ class FusionBase(object):
                         longer.append(path + [nxt])
             frontier = longer
 
+    def chain_profile(self, path, run=None, row_factor=None):
+        """The profile the reference's examples compute from one ``chain()`` path (examples/dicty_chaining.py:40-53):
+        objects of ``path[0]`` expressed over the objects of ``path[-1]``,  G_first (S_01 S_12 ...) G_last^T  with the
+        backbone of the FIRST relation of every hop; a single-type path gives the factor itself.  ``row_factor`` replaces
+        the fitted factor of ``path[0]`` (e.g. a DfmfTransform projection of new objects).  The n_first x n_last product
+        runs on the GPU (device_ops.gsg)."""
+        run = self._run_index(run)
+        first = self.factors_[path[0]][run] if row_factor is None else row_factor
+        if len(path) == 1:
+            return first
+        middle = None
+        for a, b in zip(path[:-1], path[1:]):
+            hop = self.backbones_[self.fusion_graph.get_relations(a, b)[0]][run]
+            middle = hop if middle is None else np.dot(middle, hop)
+        return device_ops.gsg(first, middle, self.factors_[path[-1]][run], getattr(self, "_engine_kwargs", None))
+
     def __repr__(self):
         shown = ', '.join('{}={}'.format(k, v) for k, v in self._params.items())
         return '{}({})'.format(type(self).__name__, shown)
@@ -109,7 +126,7 @@ class FusionFit(FusionBase):
         G1 = self.factor(relation.row_type, run)
         S12 = self.backbone(relation, run)
         G2 = self.factor(relation.col_type, run)
-        approx = np.dot(G1, np.dot(S12, G2.T))
+        approx = device_ops.gsg(G1, S12, G2, getattr(self, "_engine_kwargs", None))
         return relation.postprocessor(approx) if relation.postprocessor else approx
 
     def complete(self, relation, run=None):
