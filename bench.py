@@ -39,7 +39,7 @@ def parse():
     # (not "--n": torch.distributed.run's own parser treats it as an ambiguous abbreviation of --nnodes / --nproc-per-node)
     ap.add_argument("--size", dest="n", type=int, default=0, help="objects per type (0 = 81920, shrunk if HBM is short)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--split-terms", default="2", help="1..3, auto or centred1 (operand form of the factors, include/fz_fusion.h)")
+    ap.add_argument("--split-terms", default="auto", help="1..3, auto or centred1 (operand form of the factors, include/fz_fusion.h)")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of host time the CPU arm may spend on its samples")
     ap.add_argument("--cpu-sizes", default="4096,8192,16384", help="objects per type of the CPU arm's bounded samples")
     ap.add_argument("--no-e2e", action="store_true")

@@ -312,6 +312,7 @@ class Engine : public EngineBase {
   int terms_ = 2;           // split terms of the factor operand: 1..3 plain form; FZ_TERMS_AUTO / FZ_TERMS_CENTRED1: centred form
   int gs_terms_ = 2;        // terms stored in Gs (the centred forms always keep [hi | lo])
   bool centred_ = false;    // mean-centred operand form for the fused dfmf products (terms_ <= 0)
+  bool no_corr_ = false;    // FZ_NO_CORR=1 (studies / tests only): single-term kernel WITHOUT the first-order correction of M
   bool single_now_ = false; // this iteration's fused products use the single-term kernel (umma_fused1.cuh) + M correction
   // ---- FZ_TERMS_AUTO: which kernel may run is decided from measurements (gate_measure / gate_decide)
   int64_t it_count_ = 0;            // dfmf iterations run on this handle
@@ -609,6 +610,7 @@ class Engine : public EngineBase {
     }
     err_acc_.alloc(8);
     if (const char* cs = getenv("FZ_FUSED_CSPLIT")) fused_csplit_ = atoi(cs);
+    if (const char* nc = getenv("FZ_NO_CORR")) no_corr_ = (nc[0] == '1');
     if (gs_terms_ != 2) fused_ = false;
     if (const char* na = getenv("FZ_NO_AUX")) use_aux_ = !(na[0] == '1');
     if (const char* ng = getenv("FZ_NO_GRAPH")) use_graph_ = !(ng[0] == '1');
@@ -1215,7 +1217,7 @@ class Engine : public EngineBase {
     const float* centre = nullptr;
     if (centred) {     // G = 1 c^T + D with c the column means; the bf16 terms represent D
       col_sum_partial<T><<<t.centre_chunks, 256, 0, st>>>(cur(t), t.k, t.n, t.k, t.centre_rows_per_chunk, t.centre_part.template as<double>());
-      finish_centre<<<1, 64, 0, st>>>(t.centre_part.template as<double>(), t.centre_chunks, t.k, t.n, t.centre.template as<float>());
+      finish_centre<<<1, 1024, 0, st>>>(t.centre_part.template as<double>(), t.centre_chunks, t.k, t.n, t.centre.template as<float>());
       launches += 2;
       centre = t.centre.template as<float>();
     }
@@ -1234,7 +1236,7 @@ class Engine : public EngineBase {
     dim3 g(t.gram_chunks, nblk(t.k, 64), nblk(t.k, 64));
     gram_partial<T><<<g, 256, 0, st>>>(Gl, t.k, Gl, t.k, t.gram_part.template as<double>(), t.rows_loc, t.k, t.k,
                                        t.gram_rows_per_chunk, 0);
-    reduce_partials<<<nblk((long long)t.k * t.k, 32), 256, 0, st>>>(t.gram_part.template as<double>(), t.gram_raw, t.gram_chunks,
+    reduce_partials<<<nblk((long long)t.k * t.k, 32), kRedThreads, 0, st>>>(t.gram_part.template as<double>(), t.gram_raw, t.gram_chunks,
                                                                      (long long)t.k * t.k);
     launches += 2;
   }
@@ -1271,8 +1273,8 @@ class Engine : public EngineBase {
     gram_partial<T><<<g, 256, 0, st>>>(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.A.template as<T>(), Tj.k, r.M_part.template as<double>(),
                                        r.rows_loc, Ti.k, Tj.k, r.m_rows_per_chunk, 0);
     int chunks = r.m_chunks;
-    if (single_now_ && r.storage == FZ_BF16) { corr_M(r, st); chunks += r.corr_chunks; }
-    reduce_partials<<<nblk((long long)Ti.k * Tj.k, 32), 256, 0, st>>>(r.M_part.template as<double>(), r.M_raw, chunks,
+    if (single_now_ && !no_corr_ && r.storage == FZ_BF16) { corr_M(r, st); chunks += r.corr_chunks; }
+    reduce_partials<<<nblk((long long)Ti.k * Tj.k, 32), kRedThreads, 0, st>>>(r.M_part.template as<double>(), r.M_raw, chunks,
                                                                        (long long)Ti.k * Tj.k);
     launches += 2;
   }

@@ -191,28 +191,31 @@ gram_partial(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, lo
   }
 }
 
-// out[i] = sum_c part[c][i], deterministic: block = 32 consecutive elements x 8 chunk lanes (warp w sums the
-// chunks w, w+8, ... in order), then the 8 lane sums are added in fixed order.  grid = ceil(elems / 32), 256 threads.
-__global__ void __launch_bounds__(256)
+// out[i] = sum_c part[c][i], deterministic: block = 32 consecutive elements x 32 chunk lanes (warp w sums the chunks
+// w, w+32, ... in order, four independent loads in flight), then the 32 lane sums are added in fixed order.
+// grid = ceil(elems / 32), 1024 threads.
+constexpr int kRedThreads = 1024;
+__global__ void __launch_bounds__(kRedThreads)
 reduce_partials(const double* __restrict__ part, double* __restrict__ out, int n_chunks, long long elems) {
-  __shared__ double lanes[8][32];
+  __shared__ double lanes[32][33];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const long long i = (long long)blockIdx.x * 32 + l;
-  double s0 = 0.0, s1 = 0.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (i < elems) {
     int c = w;
-    for (; c + 8 < n_chunks; c += 16) {
-      s0 += part[(long long)c * elems + i];
-      s1 += part[(long long)(c + 8) * elems + i];
+    for (; c + 96 < n_chunks; c += 128) {
+      const double v0 = part[(long long)c * elems + i], v1 = part[(long long)(c + 32) * elems + i];
+      const double v2 = part[(long long)(c + 64) * elems + i], v3 = part[(long long)(c + 96) * elems + i];
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
     }
-    if (c < n_chunks) s0 += part[(long long)c * elems + i];
+    for (; c < n_chunks; c += 32) s0 += part[(long long)c * elems + i];
   }
-  lanes[w][l] = s0 + s1;
+  lanes[w][l] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (w == 0 && i < elems) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += lanes[k][l];
+    for (int k = 0; k < 32; ++k) s += lanes[k][l];
     out[i] = s;
   }
 }
@@ -255,12 +258,13 @@ struct UpdArgs {
 };
 
 constexpr int kUpdRows = 64;    // rows of the factor per block
-constexpr int kUpdSlab = 32;    // reduction slab staged in shared memory
+// reduction slab staged in shared memory (double-buffered): 32 for fp32, 16 for fp64 (48 KB of static shared memory)
+template <class T> struct UpdCfg { static constexpr int kSlab = sizeof(T) == 4 ? 32 : 16; };
 
 // One (64 rows x 64 cols) output tile per block and q-tile; 256 threads, 4 x 4 outputs per thread:
 // per reduction step 4 broadcast reads of X and one 16-byte read of W feed 16 FMAs.
 template <class T>
-__device__ __forceinline__ void upd_accumulate(T (&acc)[4][4], const T (*Xs)[kUpdSlab + 1], const T (*Ws)[64 + 4], int ty, int tx,
+__device__ __forceinline__ void upd_accumulate(T (&acc)[4][4], const T (*Xs)[UpdCfg<T>::kSlab + 1], const T (*Ws)[64 + 4], int ty, int tx,
                                                int cmax) {
   for (int cc = 0; cc < cmax; ++cc) {
     T x[4], w[4];
@@ -278,86 +282,84 @@ __device__ __forceinline__ void upd_accumulate(T (&acc)[4][4], const T (*Xs)[kUp
 template <class T>
 __global__ void __launch_bounds__(256)
 fused_update(const UpdArgs<T> a) {
-  __shared__ T Xs[kUpdRows][kUpdSlab + 1];
-  __shared__ __align__(16) T Ws[kUpdSlab][64 + 4];
+  // The work of a block is a flat list of SLAB JOBS -- (operand X, weight W, reduction offset) -- over the relation terms and
+  // the two G * sum passes.  The next job's global loads are issued into registers before the current slab is multiplied
+  // (double-buffered shared memory), so L2 / HBM latency overlaps the FMAs instead of being paid once per slab.
+  constexpr int kUpdSlab = UpdCfg<T>::kSlab;
+  constexpr int kE = kUpdSlab * 64 / 256;     // elements of each tile a thread moves
+  __shared__ T Xs[2][kUpdRows][kUpdSlab + 1];
+  __shared__ __align__(16) T Ws[2][kUpdSlab][64 + 4];
   const int tid = threadIdx.x;
   const long long r0 = (long long)blockIdx.x * kUpdRows;
   const int ty = tid / 16, tx = tid % 16;
   const T eps = (T)2.220446049250313e-16;
 
-  auto load_x = [&](const T* X, long long ldx, int kx, int c0) {
-    for (int idx = tid; idx < kUpdRows * kUpdSlab; idx += 256) {
-      const int rr = idx / kUpdSlab, cc = idx % kUpdSlab;
-      T v = T(0);
-      if (r0 + rr < a.rows && c0 + cc < kx) v = X[(r0 + rr) * ldx + c0 + cc];
-      Xs[rr][cc] = v;
-    }
-  };
-  auto load_w = [&](const T* W, int kx, int c0, int q0) {
-    for (int idx = tid; idx < kUpdSlab * 64; idx += 256) {
-      const int cc = idx / 64, qq = idx % 64;
-      T v = T(0);
-      if (c0 + cc < kx && q0 + qq < a.kt) v = W[(long long)(c0 + cc) * a.kt + q0 + qq];
-      Ws[cc][qq] = v;
-    }
-  };
-
   for (int q0 = 0; q0 < a.kt; q0 += 64) {
-    T num[4][4], den[4][4];
+    T num[4][4], den[4][4], acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { num[i][j] = T(0); den[i][j] = T(0); }
+      for (int j = 0; j < 4; ++j) { num[i][j] = T(0); den[i][j] = T(0); acc[i][j] = T(0); }
 
-    // ---- relation terms: pos/neg parts of X W
-    for (int t = 0; t < a.n_terms; ++t) {
-      const UpdTerm<T> term = a.terms[t];
-      T acc[4][4];
+    const int slabs_g = (a.kt + kUpdSlab - 1) / kUpdSlab;
+    // job cursor: term index (n_terms = G*Nsum, n_terms + 1 = G*Dsum) and slab inside it
+    int jt = 0, jc = 0;
+    auto job_valid = [&](int t) { return t < a.n_terms + 2; };
+    auto job_slabs = [&](int t) { return t < a.n_terms ? (a.terms[t].kx + kUpdSlab - 1) / kUpdSlab : slabs_g; };
+    // skip empty terms (kx == 0 cannot happen; kept cheap)
+    T px[kE], pw[kE];
+    auto fetch = [&](int t, int c) {
+      const T* X; const T* W; long long ldx; int kx;
+      if (t < a.n_terms) { const UpdTerm<T> term = a.terms[t]; X = term.X; W = term.W; ldx = term.ldx; kx = term.kx; }
+      else { X = a.G; W = (t == a.n_terms) ? a.Nsum : a.Dsum; ldx = a.ldg; kx = a.kt; }
+      const int c0 = c * kUpdSlab;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-      for (int c0 = 0; c0 < term.kx; c0 += kUpdSlab) {
-        load_x(term.X, term.ldx, term.kx, c0);
-        load_w(term.W, term.kx, c0, q0);
-        __syncthreads();
-        upd_accumulate<T>(acc, Xs, Ws, ty, tx, min(kUpdSlab, term.kx - c0));
-        __syncthreads();
+      for (int e = 0; e < kE; ++e) {
+        const int idx = tid + e * 256;
+        const int rr = idx / kUpdSlab, cc = idx % kUpdSlab;
+        px[e] = (r0 + rr < a.rows && c0 + cc < kx) ? X[(r0 + rr) * ldx + c0 + cc] : T(0);
+        const int wc = idx / 64, wq = idx % 64;
+        pw[e] = (c0 + wc < kx && q0 + wq < a.kt) ? W[(long long)(c0 + wc) * a.kt + q0 + wq] : T(0);
       }
+    };
+    auto stash = [&](int buf) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          T v = acc[i][j];
-          if (a.scrub_terms) v = scrub(v);
-          T pp, nn;
-          sign_split(v, pp, nn);
-          num[i][j] += pp;
-          den[i][j] += nn;
-        }
-    }
-    // ---- G * Nsum (numerator) and G * Dsum (denominator)
-    for (int pass = 0; pass < 2; ++pass) {
-      const T* W = pass == 0 ? a.Nsum : a.Dsum;
-      T acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-      for (int c0 = 0; c0 < a.kt; c0 += kUpdSlab) {
-        load_x(a.G, a.ldg, a.kt, c0);
-        load_w(W, a.kt, c0, q0);
-        __syncthreads();
-        upd_accumulate<T>(acc, Xs, Ws, ty, tx, min(kUpdSlab, a.kt - c0));
-        __syncthreads();
+      for (int e = 0; e < kE; ++e) {
+        const int idx = tid + e * 256;
+        Xs[buf][idx / kUpdSlab][idx % kUpdSlab] = px[e];
+        Ws[buf][idx / 64][idx % 64] = pw[e];
       }
+    };
+    int buf = 0;
+    fetch(jt, jc);
+    while (job_valid(jt)) {
+      stash(buf);
+      __syncthreads();
+      // advance the cursor and prefetch the next job
+      int nt = jt, nc = jc + 1;
+      if (nc >= job_slabs(jt)) { nt = jt + 1; nc = 0; }
+      if (job_valid(nt)) fetch(nt, nc);
+      upd_accumulate<T>(acc, Xs[buf], Ws[buf], ty, tx, kUpdSlab);     // zero padding beyond kx adds nothing
+      if (nt != jt) {            // the term is complete: fold it into num / den
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (pass == 0) num[i][j] += acc[i][j];
-          else den[i][j] += acc[i][j];
-        }
+          for (int j = 0; j < 4; ++j) {
+            T v = acc[i][j];
+            acc[i][j] = T(0);
+            if (jt < a.n_terms) {
+              if (a.scrub_terms) v = scrub(v);
+              T pp, nn;
+              sign_split(v, pp, nn);
+              num[i][j] += pp;
+              den[i][j] += nn;
+            } else if (jt == a.n_terms) num[i][j] += v;
+            else den[i][j] += v;
+          }
+      }
+      jt = nt;
+      jc = nc;
+      buf ^= 1;     // the other buffer was last read one job ago, behind this job's barrier
     }
     // ---- additive pairs + the update itself
 #pragma unroll
@@ -377,6 +379,7 @@ fused_update(const UpdArgs<T> a) {
         a.Gnew[row * a.ldg + q] = g * sqrt(nu / max(de, eps));
       }
     }
+    __syncthreads();
   }
 }
 
@@ -568,14 +571,22 @@ col_sum_partial(const T* __restrict__ G, long long ldg, long long n, int k, long
   __syncthreads();
   if (lane == 0 && q < k) part[(long long)blockIdx.x * k + q] = red[0][q] + red[1][q] + red[2][q] + red[3][q];
 }
-// centre[q] = (sum_chunks part[chunk][q]) / n   (fixed order); one block of 64 threads
-__global__ void finish_centre(const double* __restrict__ part, int chunks, int k, long long n, float* __restrict__ centre) {
-  const int q = threadIdx.x;
-  if (q >= 64) return;
+// centre[q] = (sum_chunks part[chunk][q]) / n; one block of 1024 threads = 16 chunk lanes x 64 columns, fixed order
+__global__ void __launch_bounds__(1024)
+finish_centre(const double* __restrict__ part, int chunks, int k, long long n, float* __restrict__ centre) {
+  __shared__ double red[16][64];
+  const int q = threadIdx.x & 63, lane = threadIdx.x >> 6;
   double s = 0.0;
   if (q < k)
-    for (int c = 0; c < chunks; ++c) s += part[(long long)c * k + q];
-  centre[q] = (q < k && n > 0) ? (float)(s / (double)n) : 0.f;
+    for (int c = lane; c < chunks; c += 16) s += part[(long long)c * k + q];
+  red[lane][q] = s;
+  __syncthreads();
+  if (lane == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += red[i][q];
+    centre[q] = (q < k && n > 0) ? (float)(t / (double)n) : 0.f;
+  }
 }
 // row sums (one warp per row) and partial column sums of a stored relation, fp64 accumulation -> fp32
 template <class XT>

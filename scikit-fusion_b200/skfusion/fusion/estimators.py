@@ -91,7 +91,7 @@ class FusionBase(object):
             return first
         middle = None
         for a, b in zip(path[:-1], path[1:]):
-            hop = self.backbones_[self.fusion_graph.get_relations(a, b)[0]][run]
+            hop = self.backbones_[next(iter(self.fusion_graph.get_relations(a, b)))][run]
             middle = hop if middle is None else np.dot(middle, hop)
         return device_ops.gsg(first, middle, self.factors_[path[-1]][run], getattr(self, "_engine_kwargs", None))
 

@@ -32,7 +32,7 @@ engine_options = {
     "device": int(os.environ.get("SKFUSION_B200_DEVICE", "0")),
     "dtype": os.environ.get("SKFUSION_B200_DTYPE", "auto"),
     "storage": os.environ.get("SKFUSION_B200_STORAGE") or None,
-    "split_terms": _terms(os.environ.get("SKFUSION_B200_SPLIT_TERMS", "2")),
+    "split_terms": _terms(os.environ.get("SKFUSION_B200_SPLIT_TERMS", "auto")),
     "device_init": {"1": True, "0": False}.get(os.environ.get("SKFUSION_B200_DEVICE_INIT", ""), "auto"),
     "n_gpus": int(os.environ.get("SKFUSION_B200_N_GPUS", "1")),
 }
