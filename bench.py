@@ -290,6 +290,7 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     launches0 = eng.launches
+    operand0 = eng.operand_stats()
     eng.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -305,6 +306,9 @@ def gpu_arm(args):
     elapsed_ms = e0.elapsed_time(e1)
     n_prof, prof_ms, prof_bytes, prof_alg = eng.profile_read()
     eng.profile(False)
+    operand = eng.operand_stats()
+    timed_single = operand["single"] - operand0["single"]
+    timed_two = operand["two_term"] - operand0["two_term"]
     launches = eng.launches - launches0
     if world > 1:
         tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
@@ -329,9 +333,16 @@ def gpu_arm(args):
     alg_bytes_per_launch = prof_alg / max(1, n_prof)
     traffic, traffic_note = None, None
     kernel_name = "umma_fused_t_kernel" if os.environ.get("FZ_FUSED_VER", "3") == "4" else "umma_fused_kernel"
+    if timed_single > 0 and timed_single >= timed_two:
+        kernel_name = "umma_fused1_kernel"
     try:   # dram__bytes_read+write per launch from the committed ncu --set full capture, scaled to this launch size
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01b_ncu_traffic.json")))[kernel_name]
-        if fused_kernel_active(args):
+        cap = None
+        for name in ("r02_ncu_traffic.json", "r01b_ncu_traffic.json"):
+            table = json.load(open(os.path.join(ROOT, "profiles", name))) if os.path.exists(os.path.join(ROOT, "profiles", name)) else {}
+            if kernel_name in table:
+                cap = table[kernel_name]
+                break
+        if fused_kernel_active(args) and cap is not None:
             traffic = cap["traffic_over_algorithmic"] * alg_bytes_per_launch
             traffic_note = "ncu capture at n=40960: %.4f x algorithmic bytes (%s), scaled to this launch" % (
                 cap["traffic_over_algorithmic"], cap["raw"])
@@ -352,13 +363,15 @@ def gpu_arm(args):
         # relation element = 256 flop/B, above the measured ridge (sustained bf16 / HBM), and under random operands the
         # board sits at its power cap.  Reported next to the algorithmic (HBM) roofline, never instead of it.
         tf_peak = float(peaks.get("bf16_tflops_sustained", 0.0)) or None
-        executed = 2.0 * 128.0 * (1 if args.split_terms == 'centred1' else 2) * (alg_bytes_per_launch / 2.0)      # flop per launch
+        # 2 products x 2 flop x 64 columns per relation element and split term, weighted by the kernels that actually ran
+        terms_run = (timed_single + 2.0 * timed_two) / max(1, timed_single + timed_two)
+        executed = 2.0 * 128.0 * terms_run * (alg_bytes_per_launch / 2.0)      # flop per launch
         tf = executed / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
         roofline["kernel"] = kernel_name + " (tcgen05/TMA, A and B from one stream of R)"
         roofline["tensor_executed"] = {"achieved": round(tf, 1), "peak": tf_peak, "unit": "TFLOP/s",
                                        "frac": round(tf / tf_peak, 4) if tf_peak else None,
-                                       "note": "executed tensor work incl. the 2-term bf16 split (256 flop per relation byte); "
-                                               "peak = MEASURED_PEAKS.json bf16_tflops_sustained"}
+                                       "note": "executed tensor work (128 flop per relation byte and split term; %.2f terms on average "
+                                               "over the timed iterations); peak = MEASURED_PEAKS.json bf16_tflops_sustained" % terms_run}
 
     # ---- e2e: the same fit through the C ABI with HOST buffers (pinned), H2D of the relations and D2H of the
     # factors / backbones inside the timed region.
@@ -367,7 +380,6 @@ def gpu_arm(args):
     Sf = {key: [eng.get_backbone(i) for i in ids] for key, ids in rel_ids.items()}
     check = _check_sums(Gf, Sf, args.warmup + args.steps)
     del Gf, Sf
-    operand = eng.operand_stats()
     e2e = None
     eng.close()                      # frees the engine's buffers and drops its references to the borrowed relations
     if not args.no_e2e:
@@ -393,7 +405,8 @@ def gpu_arm(args):
                        "cache": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (10.0 * n * (hi - lo) * 2 / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "check": check, "parity": parity,
             "operand_form": {"split_terms": args.split_terms, "single_term_iterations": operand["single"],
-                             "two_term_iterations": operand["two_term"], "gate_error_estimate": operand["err"],
+                             "two_term_iterations": operand["two_term"], "timed_single_term_iterations": timed_single,
+                             "timed_two_term_iterations": timed_two, "gate_error_estimate": operand["err"],
                              "gate_cond_estimate": operand["cond"]},
             "clocks": sampler.summary(),
         }

@@ -282,21 +282,27 @@ struct BackboneJob {
   double* t5;            // k_j x k_j  = S^T G_i^T G_i S
   T* W1;                 // k_j x k_i  = S^T in the compute dtype  (tmp1 = A S^T)
   T* W4;                 // k_i x k_j  = S                         (tmp4 = B S)
-  double* work;          // 2 * max(k_i,k_j)^2
+  double* work;          // 6 * max(k_i,k_j)^2 (three matrices per CTA of the relation's pair)
   int ki, kj;
   int solve;             // 1: compute S from M_raw; 0: S is given (transform)
   int scrub;             // dfmf: nan_to_num on every k x k product
 };
 
+// grid = (relations, 2): both CTAs of a relation solve S (cheap, and it saves a grid-wide dependency); CTA 0 publishes S and
+// the compute-dtype copies and forms t2 = S gram_j S^T, CTA 1 forms t5 = S^T gram_i S -- the chain sits on the critical path
+// of every iteration (sharded runs: right behind the all-reduce), so its two independent halves run side by side.
 template <class T>
 __global__ void __launch_bounds__(kChainThreads)
 backbone_chain(const BackboneJob<T>* __restrict__ jobs) {
   const BackboneJob<T> job = jobs[blockIdx.x];
+  const int half = blockIdx.y;
   const int ki = job.ki, kj = job.kj;
   const int tid = threadIdx.x, nth = blockDim.x;
   const int km = max(ki, kj);
-  double* U = job.work;
-  double* Vw = job.work + (long long)km * km;
+  double* U = job.work + (long long)half * 3 * km * km;
+  double* Vw = U + (long long)km * km;
+  double* Sl = Vw + (long long)km * km;                      // CTA 1's private copy of S
+  double* S = (half == 0 || !job.solve) ? job.S : Sl;
   extern __shared__ double chain_stage[];
   double* stage = (km <= kChainSmemDim) ? chain_stage : nullptr;
   if (job.solve) {
@@ -305,30 +311,33 @@ backbone_chain(const BackboneJob<T>* __restrict__ jobs) {
     __syncthreads();
     block_mm(U, kj, Vw, kj, false, job.P_j, kj, false, ki, kj, kj, stage);
     __syncthreads();
-    block_mm(job.S, kj, job.P_i, ki, false, U, kj, false, ki, kj, ki, stage);
+    block_mm(S, kj, job.P_i, ki, false, U, kj, false, ki, kj, ki, stage);
     __syncthreads();
-    for (int o = tid; o < ki * kj; o += nth) job.S[o] = scrub(job.S[o]);
+    for (int o = tid; o < ki * kj; o += nth) S[o] = scrub(S[o]);
     __syncthreads();
   }
-  // t2 = S gram_j S^T
-  block_mm(U, kj, job.S, kj, false, job.gram_j, kj, false, ki, kj, kj, stage);
-  __syncthreads();
-  block_mm(job.t2, ki, U, kj, false, job.S, kj, true, ki, ki, kj, stage);
-  __syncthreads();
-  // t5 = S^T gram_i S
-  block_mm(U, ki, job.S, kj, true, job.gram_i, ki, false, kj, ki, ki, stage);
-  __syncthreads();
-  block_mm(job.t5, kj, U, ki, false, job.S, kj, false, kj, kj, ki, stage);
-  __syncthreads();
-  if (job.scrub) {
-    for (int o = tid; o < ki * ki; o += nth) job.t2[o] = scrub(job.t2[o]);
-    for (int o = tid; o < kj * kj; o += nth) job.t5[o] = scrub(job.t5[o]);
-  }
-  for (int o = tid; o < ki * kj; o += nth) {
-    const int a = o / kj, b = o % kj;
-    const double s = job.S[o];
-    job.W4[o] = (T)s;
-    job.W1[(long long)b * ki + a] = (T)s;
+  if (half == 0) {
+    // t2 = S gram_j S^T
+    block_mm(U, kj, S, kj, false, job.gram_j, kj, false, ki, kj, kj, stage);
+    __syncthreads();
+    block_mm(job.t2, ki, U, kj, false, S, kj, true, ki, ki, kj, stage);
+    __syncthreads();
+    if (job.scrub)
+      for (int o = tid; o < ki * ki; o += nth) job.t2[o] = scrub(job.t2[o]);
+    for (int o = tid; o < ki * kj; o += nth) {
+      const int a = o / kj, b = o % kj;
+      const double s = S[o];
+      job.W4[o] = (T)s;
+      job.W1[(long long)b * ki + a] = (T)s;
+    }
+  } else {
+    // t5 = S^T gram_i S
+    block_mm(U, ki, S, kj, true, job.gram_i, ki, false, kj, ki, ki, stage);
+    __syncthreads();
+    block_mm(job.t5, kj, U, ki, false, S, kj, false, kj, kj, ki, stage);
+    __syncthreads();
+    if (job.scrub)
+      for (int o = tid; o < kj * kj; o += nth) job.t5[o] = scrub(job.t5[o]);
   }
 }
 

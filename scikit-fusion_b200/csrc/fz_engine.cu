@@ -305,7 +305,7 @@ class Engine : public EngineBase {
   ncclComm_t comm_ = nullptr;
   cudaStream_t comm_stream_ = nullptr;
   cudaEvent_t ev_c0_ = nullptr, ev_c1_ = nullptr, ev_gram_ = nullptr, ev_gram_done_ = nullptr;
-  std::vector<cudaEvent_t> ev_upd_, ev_gather_;
+  std::vector<cudaEvent_t> ev_upd_, ev_gather_, ev_rs_;
   std::vector<char> gather_pending_;
   int64_t gram_count_ = 0;      // leading doubles of small_ that hold the Gram sums (all-reduced ahead of the rest)
   bool pinv_done_ = false;      // this iteration's pseudo-inverses already ran beside the products
@@ -363,6 +363,7 @@ class Engine : public EngineBase {
     for (auto e : {ev_c0_, ev_c1_, ev_gram_, ev_gram_done_}) if (e) cudaEventDestroy(e);
     for (auto e : ev_upd_) cudaEventDestroy(e);
     for (auto e : ev_gather_) cudaEventDestroy(e);
+    for (auto e : ev_rs_) cudaEventDestroy(e);
     if (aux_) cudaStreamDestroy(aux_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
@@ -587,7 +588,7 @@ class Engine : public EngineBase {
       r.W1.alloc((size_t)Ti.k * Tj.k * sizeof(T));
       r.W4.alloc((size_t)Ti.k * Tj.k * sizeof(T));
       const int km = std::max(Ti.k, Tj.k);
-      r.work.alloc((size_t)2 * km * km * 8);
+      r.work.alloc((size_t)6 * km * km * 8);
       if (r.storage == FZ_BF16) {
         std::string e;
         bool ok = make_tmap_bf16_2d(&r.tmX, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols, (uint64_t)r.ld, 64, 128, &e) &&
@@ -626,6 +627,8 @@ class Engine : public EngineBase {
     }
     ev_rel_.resize(rels_.size());
     for (auto& e : ev_rel_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_rs_.resize(rels_.size());
+    for (auto& e : ev_rs_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ev_upd_.resize(types_.size());
     ev_gather_.resize(types_.size());
     gather_pending_.assign(types_.size(), 0);
@@ -709,6 +712,12 @@ class Engine : public EngineBase {
       if (rel.theta) continue;
       CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_rel_[r], 0));            // this relation's B partial is complete
       NCCL_OK(nc.ReduceScatter(rel.B.p, rel.Bloc.p, (size_t)types_[rel.tj]->m_loc * types_[rel.ti]->k, dt, ncclSum, comm_, comm_stream_));
+      if (corr_deferred()) {      // the correction of M reads this rank's reduce-scattered rows of B
+        cudaStream_t fin = use_aux_ ? aux_ : st;
+        CUDA_OK(cudaEventRecord(ev_rs_[r], comm_stream_));
+        CUDA_OK(cudaStreamWaitEvent(fin, ev_rs_[r], 0));
+        finish_M(rel, fin, /*local_rows=*/true);
+      }
     }
     phase_products_end(algo, st);                                          // joins the fp64 reductions into st
     CUDA_OK(cudaEventRecord(ev_c0_, st));
@@ -797,9 +806,9 @@ class Engine : public EngineBase {
       product_B(r, st);
     }
     CUDA_OK(cudaEventRecord(ev_rel_[rel], st));        // A_ij and the B partial are complete here
-    if (!use_aux_) { reduce_M(r, st); if (gate_check_now_) gate_measure(r, rel, st); return; }
+    if (!use_aux_) { reduce_M(r, st, !corr_deferred()); if (gate_check_now_) gate_measure(r, rel, st); return; }
     CUDA_OK(cudaStreamWaitEvent(aux_, ev_rel_[rel], 0));
-    reduce_M(r, aux_);                                 // G_i^T A_ij overlaps the next relation's stream
+    reduce_M(r, aux_, !corr_deferred());               // G_i^T A_ij overlaps the next relation's stream
     if (gate_check_now_) gate_measure(r, rel, aux_);
   }
   void phase_products_end(int algo, cudaStream_t st) override {
@@ -1266,21 +1275,31 @@ class Engine : public EngineBase {
   // A and B from ONE stream of a bf16 relation (umma_fused.cuh).  Returns false when not applicable.
   bool product_AB_fused(RelRec& r, cudaStream_t st);
 
-  void reduce_M(RelRec& r, cudaStream_t st) {    // M = G_i[local]^T A    (fp64 accumulate)
+  void reduce_M(RelRec& r, cudaStream_t st, bool finish = true) {    // M = G_i[local]^T A    (fp64 accumulate)
     TypeRec& Ti = *types_[r.ti];
     TypeRec& Tj = *types_[r.tj];
     dim3 g(r.m_chunks, nblk(Ti.k, 64), nblk(Tj.k, 64));
     gram_partial<T><<<g, 256, 0, st>>>(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.A.template as<T>(), Tj.k, r.M_part.template as<double>(),
                                        r.rows_loc, Ti.k, Tj.k, r.m_rows_per_chunk, 0);
+    ++launches;
+    if (finish) finish_M(r, st, /*local_rows=*/false);
+  }
+  // second half of reduce_M: the first-order correction of the single-term form, then the fixed-order sum of all partials.
+  // local_rows: the correction uses this rank's reduce-scattered rows of B (sharded handles with their own communicator:
+  // 1 / world of the work, but it has to wait for the relation's reduce-scatter) instead of the full-height local partial.
+  void finish_M(RelRec& r, cudaStream_t st, bool local_rows) {
+    TypeRec& Ti = *types_[r.ti];
+    TypeRec& Tj = *types_[r.tj];
     int chunks = r.m_chunks;
-    if (single_now_ && !no_corr_ && r.storage == FZ_BF16) { corr_M(r, st); chunks += r.corr_chunks; }
+    if (single_now_ && !no_corr_ && r.storage == FZ_BF16) { corr_M(r, st, local_rows); chunks += r.corr_chunks; }
     reduce_partials<<<nblk((long long)Ti.k * Tj.k, 32), kRedThreads, 0, st>>>(r.M_part.template as<double>(), r.M_raw, chunks,
                                                                        (long long)Ti.k * Tj.k);
-    launches += 2;
+    ++launches;
   }
+  bool corr_deferred() const { return comm_ != nullptr && single_now_ && !no_corr_; }
   // Single-term operand form: G_i^T R G_j = G_i^T (R Gs_j + rowsum c_j^T) + (R^T G_i)^T lo_j, and R^T G_i is B up to second
   // order in the residuals.  The partials land behind the M partials and are summed with them in fp64.
-  void corr_M(RelRec& r, cudaStream_t st);
+  void corr_M(RelRec& r, cudaStream_t st, bool local_rows);
   // Which fused kernel runs this iteration's products (centred operand form only)
   bool choose_single() {
     if (terms_ == FZ_TERMS_CENTRED1) return true;
@@ -1468,7 +1487,7 @@ class Engine : public EngineBase {
     }
     pinv_done_ = false;
     if (!bb_host_.empty()) {
-      backbone_chain<T><<<(unsigned)bb_host_.size(), kChainThreads, kChainSmemBytes, st>>>(bb_jobs_.template as<BackboneJob<T>>());
+      backbone_chain<T><<<dim3((unsigned)bb_host_.size(), 2), kChainThreads, kChainSmemBytes, st>>>(bb_jobs_.template as<BackboneJob<T>>());
       ++launches;
     }
     type_sums<T><<<(unsigned)types_.size(), 256, 0, st>>>(sum_jobs_.template as<TypeSumJob<T>>());
@@ -1692,17 +1711,29 @@ void Engine<float>::product_GSG(int ti, int tj, const double* S_dev, void* dst, 
   CUDA_OK(cudaStreamSynchronize(st));     // the operand buffers die here
 }
 template <>
-void Engine<float>::corr_M(RelRec& r, cudaStream_t st) {
+void Engine<float>::corr_M(RelRec& r, cudaStream_t st, bool local_rows) {
   TypeRec& Ti = *types_[r.ti];
   TypeRec& Tj = *types_[r.tj];
   dim3 g(r.corr_chunks, nblk(Ti.k, 64), nblk(Tj.k, 64));
-  corr_partial<<<g, 256, 0, st>>>(r.B.template as<float>(), Ti.k, cur(Tj), Tj.k, Tj.Gs.template as<__nv_bfloat16>(), (long long)gs_terms_ * kKp,
-                                  Tj.centre.template as<float>(), r.M_part.template as<double>() + (size_t)r.m_chunks * Ti.k * Tj.k,
-                                  Tj.n, Ti.k, Tj.k, r.corr_rows_per_chunk);
+  const long long ldgs = (long long)gs_terms_ * kKp;
+  const float* B = r.B.template as<float>();
+  const float* G = cur(Tj);
+  const __nv_bfloat16* Gs = Tj.Gs.template as<__nv_bfloat16>();
+  long long rows = Tj.n;
+  int rows_per_chunk = r.corr_rows_per_chunk;
+  if (local_rows) {       // this rank's rows of type j: B after the reduce-scatter, the matching rows of the factor
+    B = r.Bloc.template as<float>();
+    G += Tj.row0 * Tj.k;
+    Gs += Tj.row0 * ldgs;
+    rows = Tj.rows_loc;
+    rows_per_chunk = (int)((((Tj.m_loc + r.corr_chunks - 1) / r.corr_chunks) + 15) / 16 * 16);
+  }
+  corr_partial<<<g, 256, 0, st>>>(B, Ti.k, G, Tj.k, Gs, ldgs, Tj.centre.template as<float>(),
+                                  r.M_part.template as<double>() + (size_t)r.m_chunks * Ti.k * Tj.k, rows, Ti.k, Tj.k, rows_per_chunk);
   ++launches;
 }
 template <>
-void Engine<double>::corr_M(RelRec&, cudaStream_t) {}
+void Engine<double>::corr_M(RelRec&, cudaStream_t, bool) {}
 template <>
 void Engine<float>::gate_measure(RelRec& r, int rel, cudaStream_t st) {
   if (r.theta || r.storage != FZ_BF16 || r.rows_loc <= 0) return;
