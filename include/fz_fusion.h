@@ -96,9 +96,11 @@ int fz_set_backbone(fz_engine* e, int rel, const void* S, int64_t ld, int src, i
  *   FZ_TERMS_CENTRED1 always the single-term kernel (no accuracy gate: for studies) */
 enum { FZ_TERMS_AUTO = 0, FZ_TERMS_CENTRED1 = -1 };
 int fz_set_split_terms(fz_engine* e, int terms);
-/* dfmf iterations run so far with the single-term / the two-term fused kernel, and the last measured operand-form error and
- * Gram condition estimate of the FZ_TERMS_AUTO gate (-1 before the first check).  Any pointer may be NULL. */
-int fz_operand_stats(fz_engine* e, int64_t* single_iters, int64_t* two_term_iters, double* err_estimate, double* cond_estimate);
+/* dfmf iterations run so far with the single-term / the two-term fused kernel, how many of them were batched with a partner
+ * handle (fz_pair_iterate), and the last measured operand-form error and Gram condition estimate of the FZ_TERMS_AUTO gate
+ * (-1 before the first check).  Any pointer may be NULL. */
+int fz_operand_stats(fz_engine* e, int64_t* single_iters, int64_t* two_term_iters, int64_t* paired_iters, double* err_estimate,
+                     double* cond_estimate);
 /* allocate workspaces, build TMA descriptors; must precede the calls below */
 int fz_finalize(fz_engine* e);
 
@@ -106,6 +108,14 @@ int fz_finalize(fz_engine* e);
 /* n_iters iterations of the multiplicative-update loop (_dfmf.py:212-296 / _dfmc.py:270-366).
  * Sharded handles need fz_comm_init (the engine then runs the collectives) or the phase calls below. */
 int fz_iterate(fz_engine* e, int algo, int n_iters, void* stream);
+/* Two restarts batched into one pass over the relations (reference: the n_run fan-out of Dfmf.fuse, dfmf.py:87-95).  e0 and
+ * e1 describe the same graph on the same device with different initial factors; e1's bf16 relations must be BORROWED from
+ * e0's device copies (fz_relation_device_ptr), both handles use a centred operand form (FZ_TERMS_AUTO / FZ_TERMS_CENTRED1).
+ * Per iteration one launch per relation multiplies each relation tile with both runs' single-term operands; iterations in
+ * which an accuracy gate measures or refuses the single-term form run one handle after the other, like two fz_iterate calls. */
+int fz_pair_iterate(fz_engine* e0, fz_engine* e1, int n_iters, void* stream);
+/* device pointer, leading dimension (elements) and dtype of the engine's copy of a relation (valid until fz_destroy) */
+int fz_relation_device_ptr(fz_engine* e, int rel, void** ptr, int64_t* ld, int* dtype);
 /* Sharded iteration, in order:  products -> [all-reduce small, reduce-scatter B] -> update ->
  * [all-gather factors].  fz_iterate == products + update when world == 1. */
 int fz_phase_products(fz_engine* e, int algo, void* stream);

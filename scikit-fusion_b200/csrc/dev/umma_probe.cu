@@ -198,7 +198,7 @@ static int run_fused_case(int rows, int cols, int ka, int kb, int csplit, int tm
   p.a_atomic = splits > 1;
   CK(cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes));
   dim3 grid((rows + 255) / 256, splits);
-  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tgj, tgi, tb, p);
+  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tgj, tgi, tb, tb, p);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> hA((size_t)rows * ka), hB((size_t)cols * kb);
@@ -250,7 +250,7 @@ static void bench_fused(int n, int skip_flush) {
     p.a_atomic = splits > 1;
     dim3 grid((n + 255) / 256, splits);
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int w = 0; w < 2; ++w) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, p);
+    for (int w = 0; w < 2; ++w) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, tb, p);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     int reps = 40;
@@ -258,10 +258,10 @@ static void bench_fused(int n, int skip_flush) {
     if (g_sustain_s > 0) {
       // warm into the power-capped regime for half the time, then measure the second half
       reps = (int)(g_sustain_s * 0.5 / 0.6e-3);
-      for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, p);
+      for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, tb, p);
     }
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, p);
+    for (int r = 0; r < reps; ++r) umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes>>>(tr, tg64, tg, tb, tb, p);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
     printf("bench FUSED%s n=%d csplit=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s\n", skip_flush == 0 ? " (tma flush)" : skip_flush == 8 ? " (red flush)" : (skip_flush == 1 ? " (probe: no RED)" : (skip_flush == 2 ? " (probe: no B MMA)" : (skip_flush == 4 ? " (probe: no A MMA)" : (skip_flush == 3 ? " (probe: no RED, no B MMA)" : (skip_flush == 6 ? " (probe: no MMA, flush on)" : (skip_flush == 16 ? " (probe: B-product 1 term)" : (skip_flush == 48 ? " (probe: both products 1 term)" : " (probe: TMA only)"))))))), n, splits, grid.x, grid.y,

@@ -162,7 +162,9 @@ class EngineBase {
   virtual void relation_norms(int rel, int axis, double* dst_host, cudaStream_t st) = 0;
   virtual void init_add_sampled_means(int t, int rel, const int32_t* idx_host, int p_c, cudaStream_t st) = 0;
   virtual void init_end() = 0;
-  virtual void operand_stats(int64_t* single_iters, int64_t* two_term_iters, double* err_estimate, double* cond_estimate) = 0;
+  virtual void pair_iterate(EngineBase* other, int n_iters, cudaStream_t st) = 0;
+  virtual void relation_device_ptr(int rel, void** ptr, int64_t* ld, int* dtype) = 0;
+  virtual void operand_stats(int64_t* single_iters, int64_t* two_term_iters, int64_t* paired_iters, double* err_estimate, double* cond_estimate) = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -262,6 +264,10 @@ class Engine : public EngineBase {
     DevBuf GsT;              // bf16 [128][ldt]: transposed operand form (umma_fused_t.cuh), fused kernel v4
     int64_t ldt = 0;
     CUtensorMap tmGT;        // box {64 cols, 128 rows}
+    DevBuf pairGs;                // batched pair of restarts: [n_pad][128] bf16 = [run 0 term | run 1 term] (held by run 0's handle)
+    CUtensorMap tmPair64, tmPair128;
+    const __nv_bfloat16* hi_ptr = nullptr;   // where the first operand term of this factor currently lives, and its leading
+    long long hi_ld = 0;                     // dimension (own Gs, or a half of the partner's pair operand)
     DevBuf centre, centre_part;   // mean-centred operand form: column means of the factor (fp32 [64]) and their partial sums
     int centre_chunks = 0;
     long long centre_rows_per_chunk = 0;
@@ -771,14 +777,21 @@ class Engine : public EngineBase {
     need_final();
     check_factors();
     if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_UNSUPPORTED, "piecewise products are for dfmf");
-    single_now_ = centred_ && choose_single();
-    gate_check_now_ = gate_enabled_ && (it_count_ < 4 || (it_count_ % 8) == 0);
-    wait_gathers(st);                                  // the factors updated by the previous iteration are whole again
-    if (gate_slot_count_ > 0) CUDA_OK(cudaMemsetAsync(gate_slots_, 0, (size_t)gate_slot_count_ * 8, st));
-    pinv_done_ = false;
+    begin_flags(st, centred_ && choose_single());
     if (!use_aux_) { grams(st, centred_); return; }
     for (auto& tp : types_)
       if (tp->need_gs) split(*tp, st, centred_);       // operand forms first: every streamed product needs them
+    begin_reductions(st);
+  }
+  bool gate_checks_next() const { return gate_enabled_ && (it_count_ < 4 || (it_count_ % 8) == 0); }
+  void begin_flags(cudaStream_t st, bool single) {
+    single_now_ = single;
+    gate_check_now_ = gate_checks_next();
+    wait_gathers(st);                                  // the factors updated by the previous iteration are whole again
+    if (gate_slot_count_ > 0) CUDA_OK(cudaMemsetAsync(gate_slots_, 0, (size_t)gate_slot_count_ * 8, st));
+    pinv_done_ = false;
+  }
+  void begin_reductions(cudaStream_t st) {
     CUDA_OK(cudaEventRecord(ev_fork_, st));
     CUDA_OK(cudaStreamWaitEvent(aux_, ev_fork_, 0));
     for (auto& tp : types_) gram_of(*tp, aux_);        // Gram matrices beside the first streamed products
@@ -805,6 +818,9 @@ class Engine : public EngineBase {
       product_A(r, st);
       product_B(r, st);
     }
+    after_product(r, rel, st);
+  }
+  void after_product(RelRec& r, int rel, cudaStream_t st) {
     CUDA_OK(cudaEventRecord(ev_rel_[rel], st));        // A_ij and the B partial are complete here
     if (!use_aux_) { reduce_M(r, st, !corr_deferred()); if (gate_check_now_) gate_measure(r, rel, st); return; }
     CUDA_OK(cudaStreamWaitEvent(aux_, ev_rel_[rel], 0));
@@ -866,6 +882,89 @@ class Engine : public EngineBase {
     for (auto& tp : types_) tp->cur ^= 1;
     CUDA_OK(cudaGetLastError());
   }
+
+  // ---------------------------------------------------------------------------------------------
+  // Two restarts batched into one pass over the relations (the reference fans n_run restarts out over
+  // joblib workers, dfmf.py:87-95).  `this` is run 0, `other` run 1: same graph, same device, the relations of run 1 borrowed
+  // from run 0 (fz_relation_device_ptr).  Both runs use the single-term centred operand form; one launch of the two-row-block
+  // fused kernel in pair mode multiplies each relation tile with both runs' operands (umma_fused.cuh), everything else runs
+  // per handle.  Iterations in which either run's accuracy gate measures, or refuses the single-term form, run unpaired.
+  void pair_iterate(EngineBase* other_base, int n_iters, cudaStream_t st) override {
+    need_final();
+    Engine<T>* other = dynamic_cast<Engine<T>*>(other_base);
+    if (other == nullptr || other == this) FZ_THROW(FZ_ERR_INVALID, "pair needs two distinct handles of the same compute dtype");
+    other->need_final();
+    if (world_ != 1 || other->world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "batched restarts run on unsharded handles");
+    if (device_ != other->device_ || types_.size() != other->types_.size() || rels_.size() != other->rels_.size())
+      FZ_THROW(FZ_ERR_INVALID, "the two handles of a pair must describe the same graph on the same device");
+    bool can_pair = centred_ && other->centred_ && use_aux_ && other->use_aux_ && fused_ && kDT == FZ_F32;
+    for (size_t t = 0; t < types_.size() && can_pair; ++t)
+      can_pair = types_[t]->n == other->types_[t]->n && types_[t]->k == other->types_[t]->k;
+    for (size_t r = 0; r < rels_.size() && can_pair; ++r) {
+      RelRec& a = *rels_[r];
+      RelRec& b = *other->rels_[r];
+      can_pair = a.ti == b.ti && a.tj == b.tj && a.theta == b.theta && (a.theta || (a.storage == FZ_BF16 && a.data == b.data && a.ld == b.ld));
+    }
+    check_factors();
+    other->check_factors();
+    for (int it = 0; it < n_iters; ++it) {
+      const bool paired = can_pair && choose_single() && other->choose_single() && !gate_checks_next() && !other->gate_checks_next();
+      if (!paired) {
+        run_one(FZ_DFMF, st);
+        other->run_one(FZ_DFMF, st);
+        continue;
+      }
+      begin_flags(st, true);
+      other->begin_flags(st, true);
+      for (size_t t = 0; t < types_.size(); ++t)
+        if (types_[t]->need_gs) split_pair((int)t, *other, st);
+      begin_reductions(st);
+      other->begin_reductions(st);
+      for (size_t r = 0; r < rels_.size(); ++r) {
+        if (rels_[r]->theta) continue;
+        product_pair(*other, (int)r, st);
+        after_product(*rels_[r], (int)r, st);
+        other->after_product(*other->rels_[r], (int)r, st);
+      }
+      phase_products_end(FZ_DFMF, st);
+      other->phase_products_end(FZ_DFMF, st);
+      phase_update(FZ_DFMF, st);
+      other->phase_update(FZ_DFMF, st);
+      ++n_paired_;
+      ++other->n_paired_;
+    }
+  }
+  void relation_device_ptr(int rel, void** ptr, int64_t* ld, int* dtype) override {
+    RelRec& r = relation(rel);
+    if (ptr) *ptr = r.data;
+    if (ld) *ld = r.ld;
+    if (dtype) *dtype = r.storage;
+  }
+  int64_t n_paired_ = 0;
+  // operand forms of both runs side by side: [n_pad][128] = [bf16(G0 - c0) | bf16(G1 - c1)]
+  void split_pair(int t, Engine<T>& other, cudaStream_t st) {
+    TypeRec& T0 = *types_[t];
+    TypeRec& T1 = *other.types_[t];
+    if (!T0.pairGs.p) {
+      T0.pairGs.alloc((size_t)T0.n_pad * 2 * kKp * 2);
+      std::string e;
+      if (!make_tmap_bf16_2d(&T0.tmPair64, T0.pairGs.p, (uint64_t)T0.n_pad, 2 * kKp, 2 * kKp, 64, 64, &e) ||
+          !make_tmap_bf16_2d(&T0.tmPair128, T0.pairGs.p, (uint64_t)T0.n_pad, 2 * kKp, 2 * kKp, 64, 128, &e))
+        FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+    }
+    for (int run = 0; run < 2; ++run) {
+      Engine<T>& E = run == 0 ? *this : other;
+      TypeRec& Tt = run == 0 ? T0 : T1;
+      col_sum_partial<T><<<Tt.centre_chunks, 256, 0, st>>>(E.cur(Tt), Tt.k, Tt.n, Tt.k, Tt.centre_rows_per_chunk, Tt.centre_part.template as<double>());
+      finish_centre<<<1, 1024, 0, st>>>(Tt.centre_part.template as<double>(), Tt.centre_chunks, Tt.k, Tt.n, Tt.centre.template as<float>());
+      __nv_bfloat16* dst = T0.pairGs.template as<__nv_bfloat16>() + run * kKp;
+      split_factor_hi<T><<<nblk(Tt.n_pad * kKp, 256), 256, 0, st>>>(E.cur(Tt), Tt.k, dst, 2 * kKp, Tt.n, Tt.n_pad, Tt.k, kKp, Tt.centre.template as<float>());
+      E.launches += 3;
+      Tt.hi_ptr = dst;
+      Tt.hi_ld = 2 * kKp;
+    }
+  }
+  void product_pair(Engine<T>& other, int rel, cudaStream_t st);
 
   void comm_small(void** ptr, int64_t* count) override {
     need_final();
@@ -1150,9 +1249,10 @@ class Engine : public EngineBase {
     ++launches;
     CUDA_OK(cudaGetLastError());
   }
-  void operand_stats(int64_t* single_iters, int64_t* two_term_iters, double* err_estimate, double* cond_estimate) override {
+  void operand_stats(int64_t* single_iters, int64_t* two_term_iters, int64_t* paired_iters, double* err_estimate, double* cond_estimate) override {
     if (single_iters) *single_iters = n_single_;
     if (two_term_iters) *two_term_iters = n_two_;
+    if (paired_iters) *paired_iters = n_paired_;
     if (err_estimate) *err_estimate = gate_e_;
     if (cond_estimate) *cond_estimate = gate_cond_est_;
   }
@@ -1233,6 +1333,8 @@ class Engine : public EngineBase {
     split_factor<T><<<nblk(t.n_pad * kKp, 256), 256, 0, st>>>(cur(t), t.k, t.Gs.template as<__nv_bfloat16>(), t.n, t.n_pad, t.k, kKp,
                                                                gs_terms_, centre);
     ++launches;
+    t.hi_ptr = t.Gs.template as<__nv_bfloat16>();
+    t.hi_ld = (long long)gs_terms_ * kKp;
     if (t.GsT.p != nullptr) {
       split_factor_t<T><<<nblk(t.n_pad, 64), 256, 0, st>>>(cur(t), t.k, t.GsT.template as<__nv_bfloat16>(), t.ldt, t.n, t.ldt, t.k);
       ++launches;
@@ -1648,7 +1750,7 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
     q.variant = 0;
     umma_fused_t_kernel<<<grid, kFtThreads, kFtSmemBytes, st>>>(r.tmX256, Tj.tmGT, r.has_tmB16 ? r.tmB16 : r.tmX256, q);
   } else {
-    umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(r.tmX, Tj.tmG, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX, p);
+    umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(r.tmX, Tj.tmG, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX, r.has_tmB ? r.tmB : r.tmX, p);
   }
   ++launches;
   prof_end(st, 2.0 * (double)r.rows_loc * (double)r.cols, /*passes=*/1);
@@ -1711,14 +1813,77 @@ void Engine<float>::product_GSG(int ti, int tj, const double* S_dev, void* dst, 
   CUDA_OK(cudaStreamSynchronize(st));     // the operand buffers die here
 }
 template <>
+void Engine<float>::product_pair(Engine<float>& other, int rel, cudaStream_t st) {
+  RelRec& r0 = *rels_[rel];
+  RelRec& r1 = *other.rels_[rel];
+  TypeRec& Ti = *types_[r0.ti];
+  TypeRec& Tj = *types_[r0.tj];
+  TypeRec& Ti1 = *other.types_[r0.ti];
+  TypeRec& Tj1 = *other.types_[r0.tj];
+  ensure_sums(r0, st);
+  FusedParams p;
+  p.A = r0.A.template as<float>();
+  p.A2 = r1.A.template as<float>();
+  p.B = r0.B.template as<float>();
+  p.B2 = r1.B.template as<float>();
+  p.lda = Tj.k;
+  p.ldb = Ti.k;
+  p.n_rows = (int)r0.rows_loc;
+  p.n_cols = (int)r0.cols;
+  p.k_a = Tj.k;
+  p.k_b = Ti.k;
+  p.gi_row0 = 0;
+  p.probe_skip_flush = 0;
+  p.b_terms = 2;
+  p.pair = 1;
+  p.tma_flush = (r0.has_tmB && r1.has_tmB) ? 1 : 0;
+  p.rowsum = r0.rowsum.template as<float>();
+  p.cj = Tj.centre.template as<float>();
+  p.cj2 = Tj1.centre.template as<float>();
+  const int pairs = (int)((r0.rows_loc + 2 * kFuTile - 1) / (2 * kFuTile));
+  const int tiles = (int)((r0.cols + kFuTile - 1) / kFuTile);
+  int splits = 1;
+  double best = -1.0;
+  for (int cand = 1; cand <= std::max(1, std::min(tiles, 64)); ++cand) {      // whole waves of one CTA per SM (as product_AB_fused)
+    const int tps = (tiles + cand - 1) / cand;
+    const int eff = (tiles + tps - 1) / tps;
+    const double waves = (double)pairs * eff / sm_count_;
+    const double score = waves / std::ceil(waves) * (1.0 - 3.0 / (tps + 3.0));
+    if (score > best + 1e-9) { best = score; splits = eff; }
+  }
+  p.tiles_per_split = (tiles + splits - 1) / splits;
+  splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.a_atomic = splits > 1 ? 1 : 0;
+  // each run's B starts from the rank-1 part of its own centred form; the column sums of the relation are shared
+  rank1_init<<<nblk(Tj.n_pad * Ti.k, 256), 256, 0, st>>>(p.B, Ti.k, Tj.n_pad, r0.cols, Ti.k, r0.colsum.template as<float>(), Ti.centre.template as<float>());
+  rank1_init<<<nblk(Tj.n_pad * Ti.k, 256), 256, 0, st>>>(p.B2, Ti.k, Tj.n_pad, r0.cols, Ti.k, r0.colsum.template as<float>(), Ti1.centre.template as<float>());
+  if (p.a_atomic) {
+    CUDA_OK(cudaMemsetAsync(p.A, 0, (size_t)r0.rows_loc * Tj.k * sizeof(float), st));
+    CUDA_OK(cudaMemsetAsync(p.A2, 0, (size_t)r0.rows_loc * Tj.k * sizeof(float), st));
+  }
+  dim3 grid(pairs, splits);
+  prof_begin(st);
+  umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(r0.tmX, Tj.tmPair64, Ti.tmPair128, p.tma_flush ? r0.tmB : r0.tmX,
+                                                            p.tma_flush ? r1.tmB : r0.tmX, p);
+  launches += 3;
+  // one pass yields both products of BOTH runs: the algorithmic bytes of the two fits it serves are twice what it streams
+  prof_end(st, 2.0 * (double)r0.rows_loc * (double)r0.cols, /*passes=*/1);
+  prof_alg_bytes += 2.0 * (double)r0.rows_loc * (double)r0.cols * (profile ? 1.0 : 0.0);
+  CUDA_OK(cudaGetLastError());
+}
+template <>
+void Engine<double>::product_pair(Engine<double>&, int, cudaStream_t) {
+  FZ_THROW(FZ_ERR_UNSUPPORTED, "batched restarts need the fp32 engine");
+}
+template <>
 void Engine<float>::corr_M(RelRec& r, cudaStream_t st, bool local_rows) {
   TypeRec& Ti = *types_[r.ti];
   TypeRec& Tj = *types_[r.tj];
   dim3 g(r.corr_chunks, nblk(Ti.k, 64), nblk(Tj.k, 64));
-  const long long ldgs = (long long)gs_terms_ * kKp;
+  const long long ldgs = Tj.hi_ld;
   const float* B = r.B.template as<float>();
   const float* G = cur(Tj);
-  const __nv_bfloat16* Gs = Tj.Gs.template as<__nv_bfloat16>();
+  const __nv_bfloat16* Gs = Tj.hi_ptr;
   long long rows = Tj.n;
   int rows_per_chunk = r.corr_rows_per_chunk;
   if (local_rows) {       // this rank's rows of type j: B after the reduce-scatter, the matching rows of the factor
@@ -2069,8 +2234,16 @@ int fz_init_add_sampled_means(fz_engine* e, int t, int rel, const int32_t* idx_h
 int fz_init_end(fz_engine* e) {
   FZ_GUARD(e, e->impl->init_end())
 }
-int fz_operand_stats(fz_engine* e, int64_t* single_iters, int64_t* two_term_iters, double* err_estimate, double* cond_estimate) {
-  FZ_GUARD(e, e->impl->operand_stats(single_iters, two_term_iters, err_estimate, cond_estimate))
+int fz_pair_iterate(fz_engine* e0, fz_engine* e1, int n_iters, void* stream) {
+  if (!e1 || !e1->impl) return FZ_ERR_INVALID;
+  FZ_GUARD(e0, e0->impl->pair_iterate(e1->impl, n_iters, (cudaStream_t)stream))
+}
+int fz_relation_device_ptr(fz_engine* e, int rel, void** ptr, int64_t* ld, int* dtype) {
+  FZ_GUARD(e, e->impl->relation_device_ptr(rel, ptr, ld, dtype))
+}
+int fz_operand_stats(fz_engine* e, int64_t* single_iters, int64_t* two_term_iters, int64_t* paired_iters, double* err_estimate,
+                     double* cond_estimate) {
+  FZ_GUARD(e, e->impl->operand_stats(single_iters, two_term_iters, paired_iters, err_estimate, cond_estimate))
 }
 
 int fz_profile(fz_engine* e, int enable) {

@@ -553,6 +553,23 @@ __global__ void split_factor(const T* __restrict__ G, long long ldg, __nv_bfloat
   }
 }
 
+// First term only of the (centred) operand form, into a buffer with its own leading dimension: the two restarts of a batched
+// pair sit side by side in one [n_pad][128] operand (umma_fused.cuh, pair mode).
+template <class T>
+__global__ void split_factor_hi(const T* __restrict__ G, long long ldg, __nv_bfloat16* __restrict__ out, long long ld_out, long long n_valid,
+                                long long n_pad, int k, int kp, const float* __restrict__ centre) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * kp) return;
+  const long long r = idx / kp;
+  const int q = (int)(idx % kp);
+  float v = 0.f;
+  if (r < n_valid && q < k) {
+    v = (float)G[r * ldg + q];
+    if (centre != nullptr) v -= centre[q];
+  }
+  out[r * ld_out + q] = __float2bfloat16_rn(v);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Mean-centred single-term operand form (umma_fused1.cuh): centre of a factor, rank-1 parts, first-order correction.
 // ------------------------------------------------------------------------------------------------

@@ -38,6 +38,13 @@ struct FusedParams {
   int b_terms;         // split terms multiplied in the B-product: 2 (default) or 1 = first term only (N = 64; validated, unused by
                        // the engine: see DESIGN.md section 4).  An fp16 first term is NOT possible: kind::f16 with a bf16 A operand
                        // and an fp16 B operand raises an illegal-instruction exception on sm_100a (profiles/r01b_mixed_format_probe.log)
+  // PAIR mode (two restarts batched into one pass over R; reference fan-out over n_run: dfmf.py:87-95):
+  // the two 64-column halves of the operands are the single-term forms of RUN 0 and RUN 1 instead of the two split terms of
+  // one factor, and the halves of every accumulator go to separate outputs (A / A2, tmB / tmB2, cj / cj2) instead of being added.
+  int pair = 0;
+  float* A2 = nullptr;
+  float* B2 = nullptr;             // red.global fallback target of run 1
+  const float* cj2 = nullptr;
   const float* rowsum = nullptr;   // mean-centred operand form (G = 1 c^T + D, the split terms represent D): row sums of R, and
   const float* cj = nullptr;       // the centre of the column factor; A += rowsum c_j^T in the epilogue (nullptr: plain form)
   int probe_skip_flush;// developer probe only (wrong results): bit0 = no reductions, bit1 = no B-product MMAs, bit2 = no A-product MMAs,
@@ -59,6 +66,7 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
                   const __grid_constant__ CUtensorMap tmGj,   // Gs_j,     bf16, box {64 cols, 64 rows}
                   const __grid_constant__ CUtensorMap tmGi,   // Gs_i,     bf16, box {64 cols, 128 rows}
                   const __grid_constant__ CUtensorMap tmB,    // B,        fp32, box {32 cols, 32 rows} (reduce target)
+                  const __grid_constant__ CUtensorMap tmB2,   // B of run 1 in pair mode (any valid map otherwise)
                   const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -90,6 +98,7 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
     ptx::prefetch_tmap(&tmGj);
     ptx::prefetch_tmap(&tmGi);
     if (p.tma_flush) ptx::prefetch_tmap(&tmB);
+    if (p.tma_flush && p.pair) ptx::prefetch_tmap(&tmB2);
     for (int s = 0; s < kFuRStages; ++s) { ptx::mbar_init(&r_full[s], 1); ptx::mbar_init(&r_empty[s], 1); }
     for (int s = 0; s < kFuGjSlots; ++s) { ptx::mbar_init(&gj_full[s], 1); ptx::mbar_init(&gj_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
@@ -262,7 +271,24 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
           ptx::mbar_arrive(&bacc_empty[gs]);
         }
         if (q0 >= p.k_b || skip_red) continue;
-        if (p.tma_flush) {
+        if (p.tma_flush && p.pair) {
+          // the halves are the partials of two different runs: one reduce each, into each run's own B
+          for (int run = 0; run < 2; ++run) {
+            const float* src = run == 0 ? hi : lo;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (ptx::elect_one()) {
+              ptx::tma_reduce_add_2d(run == 0 ? &tmB : &tmB2, my_stage, q0, brow0);
+              ptx::tma_commit_group();
+              ptx::tma_wait_read_all();
+            }
+            __syncwarp();
+          }
+        } else if (p.tma_flush) {
           // row `lane` of the warp's 32 x 32 box: 8 chunks of 16 B, chunk j stored at j ^ (lane & 7)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -278,6 +304,15 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
             ptx::tma_wait_read_all();                             // staging reusable
           }
           __syncwarp();
+        } else if (p.pair) {
+          const int bcol = brow0 + lane;
+          if (bcol < p.n_cols) {
+            float* brow = p.B + (long long)bcol * p.ldb + q0;
+            float* brow2 = p.B2 + (long long)bcol * p.ldb + q0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (q0 + i < p.k_b) { atomicAdd(brow + i, hi[i]); atomicAdd(brow2 + i, lo[i]); }
+          }
         } else {
           const int bcol = brow0 + lane;
           if (bcol < p.n_cols) {
@@ -307,7 +342,13 @@ umma_fused_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16,
           if (out != nullptr) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              if (q0 + i < p.k_a) {
+              if (q0 + i < p.k_a && p.pair) {      // two runs: separate outputs, each with its own centre
+                float v = hi[i], w = lo[i];
+                if (rank1) { v = fmaf(rs, __ldg(p.cj + q0 + i), v); w = fmaf(rs, __ldg(p.cj2 + q0 + i), w); }
+                float* out2 = p.A2 + (long long)arow * p.lda;
+                if (p.a_atomic) { atomicAdd(out + q0 + i, v); atomicAdd(out2 + q0 + i, w); }
+                else { out[q0 + i] = v; out2[q0 + i] = w; }
+              } else if (q0 + i < p.k_a) {
                 float v = hi[i] + lo[i];
                 if (rank1) v = fmaf(rs, __ldg(p.cj + q0 + i), v);
                 if (p.a_atomic) atomicAdd(out + q0 + i, v);

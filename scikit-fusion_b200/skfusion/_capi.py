@@ -23,7 +23,7 @@ FZ_TERMS_AUTO, FZ_TERMS_CENTRED1 = 0, -1
 SYMBOLS = [
     "fz_create", "fz_destroy", "fz_last_error", "fz_version", "fz_launch_count", "fz_set_shard", "fz_comm_unique_id", "fz_comm_init", "fz_group_comm_init", "fz_group_iterate",
     "fz_group_objective", "fz_add_type",
-    "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_operand_stats", "fz_finalize", "fz_iterate",
+    "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_operand_stats", "fz_finalize", "fz_iterate", "fz_pair_iterate", "fz_relation_device_ptr",
     "fz_phase_products", "fz_phase_update", "fz_phase_products_begin", "fz_phase_product_relation", "fz_phase_products_end", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
     "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete", "fz_profile_product",
     "fz_fill_uniform", "fz_profile", "fz_profile_read",
@@ -91,9 +91,12 @@ def lib():
         "fz_set_factor": (i32, [vp, i32, vp, i64, i32, i32]),
         "fz_set_backbone": (i32, [vp, i32, vp, i64, i32, i32]),
         "fz_set_split_terms": (i32, [vp, i32]),
-        "fz_operand_stats": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+        "fz_operand_stats": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double),
+                             ctypes.POINTER(ctypes.c_double)]),
         "fz_finalize": (i32, [vp]),
         "fz_iterate": (i32, [vp, i32, i32, vp]),
+        "fz_pair_iterate": (i32, [vp, vp, i32, vp]),
+        "fz_relation_device_ptr": (i32, [vp, i32, c_void_pp, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
         "fz_phase_products": (i32, [vp, i32, vp]),
         "fz_phase_update": (i32, [vp, i32, vp]),
         "fz_phase_products_begin": (i32, [vp, i32, vp]),
@@ -333,11 +336,12 @@ class Engine(object):
         self._ck(self._L.fz_set_backbone(self._h, rel, ptr, ld, code, mem))
 
     def operand_stats(self):
-        """{single, two_term: dfmf iterations run with each fused kernel; err, cond: last gate measurement}."""
-        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        """{single, two_term: dfmf iterations run with each fused kernel; paired: of those, batched with a partner handle;
+        err, cond: last gate measurement}."""
+        a, b, p = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
         e, c = ctypes.c_double(0), ctypes.c_double(0)
-        self._ck(self._L.fz_operand_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(e), ctypes.byref(c)))
-        return {"single": a.value, "two_term": b.value, "err": e.value, "cond": c.value}
+        self._ck(self._L.fz_operand_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(p), ctypes.byref(e), ctypes.byref(c)))
+        return {"single": a.value, "two_term": b.value, "paired": p.value, "err": e.value, "cond": c.value}
 
     def set_split_terms(self, terms):
         """1..3 (plain operand form), 'auto' / 0 (centred form, kernel chosen per iteration from a measured error
@@ -351,6 +355,22 @@ class Engine(object):
     # ---- loop
     def iterate(self, algo, n_iters, stream=0):
         self._ck(self._L.fz_iterate(self._h, algo, int(n_iters), ctypes.c_void_p(stream)))
+
+    def pair_iterate(self, other, n_iters, stream=0):
+        """n_iters dfmf iterations of two restarts at once (this handle = run 0, ``other`` = run 1): fz_pair_iterate."""
+        self._ck(self._L.fz_pair_iterate(self._h, other._h, int(n_iters), ctypes.c_void_p(stream)))
+
+    def relation_device_ptr(self, rel):
+        p, ld, code = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int()
+        self._ck(self._L.fz_relation_device_ptr(self._h, int(rel), ctypes.byref(p), ctypes.byref(ld), ctypes.byref(code)))
+        return p.value, ld.value, code.value
+
+    def add_relation_borrowed(self, ti, tj, ptr, ld, code):
+        """A relation that lives in another handle's device memory (same device): borrowed, never copied."""
+        rid = self._ck(self._L.fz_add_relation(self._h, ti, tj, ctypes.c_void_p(ptr), int(ld), int(code), FZ_DEVICE, int(code), 1, None, 0,
+                                               FZ_HOST))
+        self.rel_types.append((ti, tj))
+        return rid
 
     def phase_products(self, algo, stream=0):
         self._ck(self._L.fz_phase_products(self._h, algo, ctypes.c_void_p(stream)))

@@ -22,7 +22,7 @@ from .graph import DataFusionError
 
 __all__ = ['FusionBase', 'FusionFit', 'FusionTransform', 'DataFusionError', 'Dfmf', 'Dfmc', 'DfmfTransform']
 
-_ENGINE_KEYS = ("device", "dtype", "storage", "split_terms", "device_init", "n_gpus")
+_ENGINE_KEYS = ("device", "dtype", "storage", "split_terms", "device_init", "n_gpus", "batch_runs")
 
 
 class FusionBase(object):
@@ -201,17 +201,42 @@ class _Fuser(FusionFit):
         common.update(self._engine_kwargs)
         self.factors_ = defaultdict(list)
         self.backbones_ = defaultdict(list)
-        for _ in range(self.n_run):
-            if self._uses_masks:
-                G, S = solver.dfmc(R=R, M=M, Theta=T, **common)
-            else:
-                G, S = solver.dfmf(R=R, Theta=T, **common)
+
+        def keep(G, S):
             for (object_type, _), factor in G.items():
                 self.factors_[object_type].append(factor)
             for (row_type, col_type), backbones in (S or {}).items():
                 for i, relation in enumerate(fusion_graph.get_relations(row_type, col_type)):
                     self.backbones_[relation].append(backbones[i])
+
+        if self._batch_restarts(R, T):
+            engine_kwargs = {k: v for k, v in self._engine_kwargs.items() if k != "batch_runs"}
+            for G, S in solver.dfmf_runs(R, T, object_types, ranks, self.n_run, max_iter=self.max_iter, init_type=self.init_type,
+                                         random_state=self.random_state, **engine_kwargs):
+                keep(G, S)
+            return self
+        common.pop("batch_runs", None)
+        for _ in range(self.n_run):
+            if self._uses_masks:
+                G, S = solver.dfmc(R=R, M=M, Theta=T, **common)
+            else:
+                G, S = solver.dfmf(R=R, Theta=T, **common)
+            keep(G, S)
         return self
+
+    def _batch_restarts(self, R, T):
+        """Whether the n_run restarts go through solver.dfmf_runs (options.py: batch_runs)."""
+        from .options import resolve
+        opts = resolve(n_entries=solver._count_entries(R, T), **self._engine_kwargs)
+        want = opts.get("batch_runs", "auto")
+        eligible = (self.n_run > 1 and not self._uses_masks and not (self.stopping or self.stopping_system or self.compute_err or
+                                                                       self.callback)
+                    and opts["dtype"] == "float32" and opts.get("storage") in ("bfloat16", "bf16")
+                    and opts.get("split_terms") in ("auto", "centred1") and int(opts.get("n_gpus") or 1) == 1)
+        if want is True and not eligible:
+            raise ValueError("batch_runs=True needs n_run > 1, Dfmf, storage='bfloat16' on the float32 engine, split_terms "
+                             "'auto' / 'centred1', one GPU and no per-iteration hooks")
+        return eligible and want in (True, "auto")
 
 
 class Dfmf(_Fuser):

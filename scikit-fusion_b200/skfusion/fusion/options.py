@@ -17,6 +17,9 @@ Defaults can be changed process-wide (``engine_options.update(dtype='float64')``
                (default: on the GPU when a relation is already device-resident or the graph has more than
                AUTO_FP64_MAX_ENTRIES entries, otherwise with numpy on the host exactly like the reference), True, False.
                The RandomState is consumed identically either way (initializers.py).
+  batch_runs   Dfmf(n_run > 1): run the restarts on one resident copy of the relations, two restarts per pass over them
+               (solver.dfmf_runs): 'auto' (default: when the fit takes the tensor-core path with a centred operand form and has
+               no per-iteration hooks), True (insist), False (one restart after the other, each uploading the data again).
   n_gpus       GPUs of this box a Dfmf fit is spread over (default 1): the rows of every object type are split contiguously
                over devices device .. device + n_gpus - 1, driven from this one process (one host thread per GPU inside the
                library, NCCL over NVLink for the three exchanges).  Dfmc and DfmfTransform stay on
@@ -35,6 +38,7 @@ engine_options = {
     "split_terms": _terms(os.environ.get("SKFUSION_B200_SPLIT_TERMS", "auto")),
     "device_init": {"1": True, "0": False}.get(os.environ.get("SKFUSION_B200_DEVICE_INIT", ""), "auto"),
     "n_gpus": int(os.environ.get("SKFUSION_B200_N_GPUS", "1")),
+    "batch_runs": {"1": True, "0": False}.get(os.environ.get("SKFUSION_B200_BATCH_RUNS", ""), "auto"),
 }
 
 

@@ -289,6 +289,63 @@ def _fit_sharded(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_typ
             prob.close()
 
 
+def dfmf_runs(R, Theta, obj_types, obj_type2rank, n_run, max_iter=10, init_type="random_vcol", random_state=None, **engine_kwargs):
+    """``n_run`` restarts of dfmf on ONE resident copy of the relations, two restarts per pass over them (the reference fans
+    restarts out over joblib workers, each with its own copy of the data: decomposition/dfmf.py:87-95).  The restarts draw
+    their initial factors from the shared ``random_state`` one after the other, exactly like ``n_run`` sequential dfmf() calls;
+    results come back in run order as a list of (G, S).  Needs the tensor-core path (storage='bfloat16', float32 engine) and a
+    centred operand form (split_terms 'auto' / 'centred1'); no per-iteration hooks (stopping / callback) -- use dfmf() for those.
+    include/fz_fusion.h: fz_pair_iterate."""
+    opts = resolve(n_entries=_count_entries(R, Theta), **engine_kwargs)
+    if opts.get("split_terms") not in ("auto", "centred1", _capi.FZ_TERMS_AUTO, _capi.FZ_TERMS_CENTRED1):
+        raise ValueError("batched restarts need split_terms 'auto' or 'centred1'")
+    if int(opts.get("n_gpus") or 1) != 1:
+        raise ValueError("batched restarts run on one GPU")
+    sizes = count_objects(obj_types, R)
+    on_device = _init_on_device(opts, init_type, R, Theta)
+    device = _device_of(R, Theta, opts)
+    probs = []
+    try:
+        for run in range(int(n_run)):
+            prob = _Problem(opts, device)
+            probs.append(prob)
+            prob.add_types(obj_types, sizes, obj_type2rank)
+            if run == 0:
+                prob.add_blocks(R, Theta, None)
+            else:       # the other restarts read the first handle's device copies of every matrix
+                first, rid = probs[0], 0
+                for key, ids in first.rel_ids.items():
+                    prob.rel_ids[key] = [prob.engine.add_relation_borrowed(prob.type_id[key[0]], prob.type_id[key[1]],
+                                                                           *first.engine.relation_device_ptr(i)) for i in ids]
+                    rid += len(ids)
+                for key, mats in Theta.items():
+                    for _ in mats:
+                        prob.engine.add_relation_borrowed(prob.type_id[key[0]], prob.type_id[key[1]],
+                                                          *first.engine.relation_device_ptr(rid))
+                        rid += 1
+            if on_device:
+                prob.engine.finalize()
+                initialize_on_device(prob.engine, prob.type_id, {key: ids[0] for key, ids in prob.rel_ids.items()}, list(obj_types),
+                                     obj_type2rank, list(R.keys()), sizes, init_type, random_state)
+            else:
+                first_mats = {key: _host_view(mats[0]) for key, mats in R.items()} if init_type != "random" else {}
+                G0 = initialize(obj_types, sizes, obj_type2rank, first_mats, init_type, random_state)
+                for t in obj_types:
+                    prob.engine.set_factor(prob.type_id[t], G0[t, t])
+                prob.engine.finalize()
+        if max_iter > 0:
+            for a in range(0, len(probs) - 1, 2):
+                probs[a].engine.pair_iterate(probs[a + 1].engine, max_iter)
+            if len(probs) % 2:
+                probs[-1].engine.iterate(_capi.FZ_DFMF, max_iter)
+        return [(prob.factors(), prob.backbones()) for prob in probs]
+    finally:
+        if probs:
+            _record(probs[0].engine, n_gpus=1, batched_runs=len(probs))
+        for prob in reversed(probs):      # the first handle owns the relations the others borrow: it goes last
+            prob.close()
+
+
 def _init_on_device(opts, init_type, R, Theta):
     """Where random_c / random_vcol compute their column means (options.py: device_init)."""
     if init_type == "random":
