@@ -616,7 +616,7 @@ def transform_workload(args):
         "metric": "transform rows*iterations/sec, BASELINE config C5", "value": round(n_new * iters / (total_ms * 1e-3), 1),
         "unit": "rows*it/s", "n_gpus": 1, "iterations": iters, "wall_ms": round(total_ms, 3),
         "prepare_ms": round(prep_ms, 3), "iterate_ms": round(iter_ms, 3), "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "transform: %d new rows of type 0 x 4 relations %d x %d bf16 (%.1f GB), rank 64, %d-term bf16 "
+        "config": {"workload": "transform: %d new rows of type 0 x 4 relations %d x %d bf16 (%.1f GB), rank 64, split_terms=%s: 2-term bf16 "
                                "split of the frozen operand G_j S^T, %d iterations" % (n_new, n_new, n, 4.0 * n_new * n * 2 / 1e9,
                                                                                      args.split_terms, iters)},
         "gpu_launches": launches,

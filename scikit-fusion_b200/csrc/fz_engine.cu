@@ -672,6 +672,7 @@ class Engine : public EngineBase {
         if (graph_exec_[algo] == nullptr || graph_parity_[algo] != parity) {
           if (graph_exec_[algo]) { cudaGraphExecDestroy(graph_exec_[algo]); graph_exec_[algo] = nullptr; }
           const int64_t before = launches;
+          const int64_t c_single = n_single_, c_two = n_two_, c_it = it_count_;     // capture executes nothing: undo its counting
           cudaGraph_t graph = nullptr;
           CUDA_OK(cudaStreamBeginCapture(gstream_, cudaStreamCaptureModeThreadLocal));
           try {
@@ -688,11 +689,18 @@ class Engine : public EngineBase {
           if (ie != cudaSuccess) FZ_THROW(FZ_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
           graph_launches_[algo] = launches - before;
           launches = before;                      // capture does not execute anything
+          n_single_ = c_single;
+          n_two_ = c_two;
+          it_count_ = c_it;
           graph_parity_[algo] = parity;
         }
         for (int g = 0; g < pairs; ++g) CUDA_OK(cudaGraphLaunch(graph_exec_[algo], gstream_));
         launches += graph_launches_[algo] * pairs;
         done += 2 * pairs;
+        if (algo == FZ_DFMF) {
+          (single_now_ ? n_single_ : n_two_) += 2 * pairs;
+          it_count_ += 2 * pairs;
+        }
         CUDA_OK(cudaEventRecord(ev_gjoin_, gstream_));
         CUDA_OK(cudaStreamWaitEvent(st, ev_gjoin_, 0));
       }
