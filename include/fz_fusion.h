@@ -78,6 +78,8 @@ int fz_add_type(fz_engine* e, int64_t n, int k);
  *   data        rows_local x n_tj matrix of `src` dtype (rows_local = n_ti unless sharded)
  *   storage     dtype kept on the device: FZ_F64 / FZ_F32 (SIMT fp path) or FZ_BF16 (tensor-core path,
  *               needs ld % 8 == 0 when borrowed; the engine pads its own copies)
+ *   borrow      1: use the caller's buffer in place -- device memory, or (mem = FZ_HOST) PINNED host memory, which is then read
+ *               over PCIe every iteration: the out-of-core mode for relations that do not fit HBM
  *   mask        optional rows_local x n_tj uint8 (non-zero = unknown entry, dfmc), NULL otherwise
  * returns the relation id (>= 0), in insertion order. */
 int fz_add_relation(fz_engine* e, int ti, int tj, const void* data, int64_t ld, int src, int mem, int storage,
@@ -190,6 +192,9 @@ int fz_fill_uniform(void* dst, int dtype, int64_t ld, int64_t rows, int64_t cols
  * Means follow numpy.nanmean (NaN skipped, +-inf included), summed in fp64; a row / column without any known entry takes
  * the matrix mean.  Masked arrays stay a host (numpy) feature. */
 int fz_fill_unknown(void* data, int dtype, int64_t ld, int64_t rows, int64_t cols, int mode, double value, void* stream);
+/* mask[r][c] = 1 where the DEVICE-resident matrix holds a non-finite entry: the completion mask Dfmc takes from numpy masked
+ * arrays on the host (skfusion/fusion/decomposition/dfmc.py:69-94), extracted without leaving the GPU (before the fill). */
+int fz_unknown_mask(const void* data, int dtype, int64_t ld, int64_t rows, int64_t cols, uint8_t* mask, int64_t mask_ld, void* stream);
 
 #ifdef __cplusplus
 }

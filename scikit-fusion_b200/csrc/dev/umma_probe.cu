@@ -461,6 +461,7 @@ static int main_fused_t(int variant, int nbench) {
 }
 
 
+static int g_dyn_chunk = 0;   // units per dynamic chunk of the fused1 schedule (0 = static only)
 // ---- v5 (single-term, mean-centred operand form, 4 row blocks per CTA): A = X Gs_j + rowsum c_j^T, B = B0 + X^T Gs_i
 static int run_fused1_case(int rows, int cols, int ka, int kb, int csplit, int tma_flush = 1, int gi_row0 = 0, bool rank1 = true) {
   const int N = 128;   // operand rows hold [hi | lo]; the kernel must read the hi half only
@@ -513,6 +514,8 @@ static int run_fused1_case(int rows, int cols, int ka, int kb, int csplit, int t
   Fused1Params p;
   p.A = dA; p.B = dB; p.lda = ka; p.ldb = kb; p.rowsum = rank1 ? dRs : nullptr; p.cj = dCj; p.n_rows = rows; p.n_cols = cols;
   p.k_a = ka; p.k_b = kb; p.gi_row0 = gi_row0; p.probe = 0; p.tma_flush = (flush_b ? 1 : 0) | (flush_a ? 2 : 0);
+  int* dCtr; CK(cudaMalloc(&dCtr, 4)); CK(cudaMemset(dCtr, 0, 4));
+  p.work_counter = g_dyn_chunk > 0 ? dCtr : nullptr; p.dyn_chunk = g_dyn_chunk;
   CK(cudaFuncSetAttribute(umma_fused1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF1SmemBytes));
   const int splits = csplit;       // number of CTAs of the persistent grid
   umma_fused1_kernel<<<csplit, kF1Threads, kF1SmemBytes>>>(tr, tgj, tgi, tb, ta, p);
@@ -535,8 +538,9 @@ static int run_fused1_case(int rows, int cols, int ka, int kb, int csplit, int t
       mb = fmax(mb, fabs(s)); eb = fmax(eb, fabs(s - hB[(size_t)c * kb + q]));
     }
   const bool good = ea / ma < 2e-5 && eb / mb < 2e-5;
-  printf("fused1 rows=%d cols=%d ka=%d kb=%d ctas=%d flush=%d gi_row0=%d rank1=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb,
-         splits, p.tma_flush, gi_row0, (int)rank1, ea / ma, eb / mb, good ? "OK" : "FAIL");
+  printf("fused1 rows=%d cols=%d ka=%d kb=%d ctas=%d dyn_chunk=%d flush=%d gi_row0=%d rank1=%d : A rel=%.3g  B rel=%.3g  %s\n", rows, cols, ka, kb,
+         splits, g_dyn_chunk, p.tma_flush, gi_row0, (int)rank1, ea / ma, eb / mb, good ? "OK" : "FAIL");
+  cudaFree(dCtr);
   cudaFree(dX); cudaFree(dGj); cudaFree(dGi); cudaFree(dA); cudaFree(dB); cudaFree(dRs); cudaFree(dCs); cudaFree(dCj); cudaFree(dCi);
   return good ? 0 : 1;
 }
@@ -560,19 +564,21 @@ static void bench_fused1(int n, int probe, int csplit = 1) {
   Fused1Params p;
   p.A = dA; p.B = dB; p.lda = k; p.ldb = k; p.rowsum = dRs; p.cj = dC; p.n_rows = n; p.n_cols = n; p.k_a = k; p.k_b = k; p.gi_row0 = 0;
   p.probe = probe; p.tma_flush = 3;
+  int* dCtr; CK(cudaMalloc(&dCtr, 4)); CK(cudaMemset(dCtr, 0, 4));
+  p.work_counter = g_dyn_chunk > 0 ? dCtr : nullptr; p.dyn_chunk = g_dyn_chunk;
   dim3 grid(csplit > 0 ? csplit : 148);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  for (int w = 0; w < 2; ++w) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, ta, p);
+  for (int w = 0; w < 2; ++w) { if (p.work_counter) cudaMemsetAsync(p.work_counter, 0, 4); umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, ta, p); }
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   int reps = 40;
   float ms;
   if (g_sustain_s > 0) {
     reps = (int)(g_sustain_s * 0.5 / 0.6e-3);
-    for (int r = 0; r < reps; ++r) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, ta, p);
+    for (int r = 0; r < reps; ++r) { if (p.work_counter) cudaMemsetAsync(p.work_counter, 0, 4); umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, ta, p); }
   }
   CK(cudaEventRecord(e0));
-  for (int r = 0; r < reps; ++r) umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, ta, p);
+  for (int r = 0; r < reps; ++r) { if (p.work_counter) cudaMemsetAsync(p.work_counter, 0, 4); umma_fused1_kernel<<<grid, kF1Threads, kF1SmemBytes>>>(tr, tg, tg, tb, ta, p); }
   CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
   CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
   printf("bench FUSED1 (persistent) probe=%d n=%d grid=%dx%d : %.3f ms  %.1f GB/s (one pass over R)  %.1f TFLOP/s executed\n", probe, n, grid.x, grid.y,
@@ -598,13 +604,26 @@ static int main_fused1(int nbench, double sustain, int csplit) {
   fails += run_fused1_case(1000, 520, 64, 40, 4, 1, 0, false);    // no rank-1 part
   fails += run_fused1_case(4096, 8192, 64, 64, 148);
   fails += run_fused1_case(5000, 3000, 64, 64, 37);
+  for (int dc : {1, 3, 16}) {       // the same shapes with a dynamic tail
+    g_dyn_chunk = dc;
+    fails += run_fused1_case(640, 256, 64, 64, 3);
+    fails += run_fused1_case(2048, 4096, 64, 64, 7);
+    fails += run_fused1_case(777, 3001, 64, 64, 13);
+    fails += run_fused1_case(4096, 8192, 64, 64, 148);
+    fails += run_fused1_case(5000, 3000, 64, 64, 37);
+    fails += run_fused1_case(3000, 2100, 33, 36, 148);
+  }
+  g_dyn_chunk = 0;
   printf("fused1 correctness: %d failing cases\n", fails);
   if (nbench > 0) {
     g_sustain_s = 0;
     for (int probe : {0, 1, 2, 4, 7}) bench_fused1(nbench, probe, csplit);   // full, no flush, no B MMA, no A MMA, TMA only
+    for (int dc : {4, 16}) { g_dyn_chunk = dc; printf("dyn_chunk=%d: ", dc); bench_fused1(nbench, 0, csplit); }
+    g_dyn_chunk = 0;
     if (sustain > 0) {
       g_sustain_s = sustain;
       for (int probe : {0, 1, 2, 4, 7}) bench_fused1(nbench, probe, csplit);
+      g_dyn_chunk = 16; printf("dyn_chunk=16: "); bench_fused1(nbench, 0, csplit); g_dyn_chunk = 0;
       bench_fused(nbench, 0);                                        // v3 for reference on the same box
     }
   }

@@ -315,9 +315,15 @@ class Engine : public EngineBase {
   std::vector<char> gather_pending_;
   int64_t gram_count_ = 0;      // leading doubles of small_ that hold the Gram sums (all-reduced ahead of the rest)
   bool pinv_done_ = false;      // this iteration's pseudo-inverses already ran beside the products
+  // operand forms of the NEXT iteration are built per type right behind that type's update (and all-gather), beside the
+  // updates of the other types, instead of in front of the next iteration's first product
+  bool presplit_valid_ = false, no_presplit_ = false;
+  cudaEvent_t ev_prep_ = nullptr;
   int terms_ = 2;           // split terms of the factor operand: 1..3 plain form; FZ_TERMS_AUTO / FZ_TERMS_CENTRED1: centred form
   int gs_terms_ = 2;        // terms stored in Gs (the centred forms always keep [hi | lo])
   bool centred_ = false;    // mean-centred operand form for the fused dfmf products (terms_ <= 0)
+  bool dyn_sched_ = true;   // FZ_NO_DYN_SCHED=1: the single-term kernel's launch is partitioned statically only
+  DevBuf sched_ctr_;        // chunk counter of its dynamic tail
   bool no_corr_ = false;    // FZ_NO_CORR=1 (studies / tests only): single-term kernel WITHOUT the first-order correction of M
   bool single_now_ = false; // this iteration's fused products use the single-term kernel (umma_fused1.cuh) + M correction
   // ---- FZ_TERMS_AUTO: which kernel may run is decided from measurements (gate_measure / gate_decide)
@@ -370,6 +376,7 @@ class Engine : public EngineBase {
     for (auto e : ev_upd_) cudaEventDestroy(e);
     for (auto e : ev_gather_) cudaEventDestroy(e);
     for (auto e : ev_rs_) cudaEventDestroy(e);
+    if (ev_prep_) cudaEventDestroy(ev_prep_);
     if (aux_) cudaStreamDestroy(aux_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
@@ -439,8 +446,20 @@ class Engine : public EngineBase {
       FZ_THROW(FZ_ERR_UNSUPPORTED, "tensor-core path supports rank <= %d (got %d, %d)", kKp, Ti.k, Tj.k);
     r->storage = storage;
     cudaStream_t st = 0;
+    if (borrow && mem == FZ_HOST) {
+      // Out-of-core relation: PINNED host memory used in place.  Every kernel that touches the relation (the TMA loads of the
+      // streamed products first of all) reads it over PCIe through the unified address space, once per iteration -- for graphs
+      // whose relations exceed HBM on the GPUs at hand.  Slow by construction (PCIe, not HBM, bounds it).
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, data) != cudaSuccess || attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) {
+        cudaGetLastError();
+        FZ_THROW(FZ_ERR_INVALID, "a borrowed host relation must be pinned (page-locked, device-mapped) memory");
+      }
+      data = attr.devicePointer;
+      mem = FZ_DEVICE;
+    }
     if (borrow) {
-      if (mem != FZ_DEVICE || src != storage) FZ_THROW(FZ_ERR_INVALID, "borrowed relations must be device memory in the storage dtype");
+      if (mem != FZ_DEVICE || src != storage) FZ_THROW(FZ_ERR_INVALID, "borrowed relations must be device (or pinned host) memory in the storage dtype");
       if (mask != nullptr) FZ_THROW(FZ_ERR_INVALID, "masked relations are rewritten by dfmc and cannot be borrowed");
       if (storage == FZ_BF16 && ((ld % 8) != 0 || ((uintptr_t)data & 15) != 0))
         FZ_THROW(FZ_ERR_INVALID, "borrowed bf16 relation needs 16-byte alignment and ld %% 8 == 0");
@@ -479,6 +498,7 @@ class Engine : public EngineBase {
     copy_in(G0, ld, src, mem, Tt.G[Tt.cur].p, Tt.k, kDT, Tt.n, Tt.k, 0);
     CUDA_OK(cudaStreamSynchronize(0));
     Tt.has_factor = true;
+    presplit_valid_ = false;
   }
 
   void set_backbone(int rel, const void* S, int64_t ld, int src, int mem) override {
@@ -618,6 +638,8 @@ class Engine : public EngineBase {
     err_acc_.alloc(8);
     if (const char* cs = getenv("FZ_FUSED_CSPLIT")) fused_csplit_ = atoi(cs);
     if (const char* nc = getenv("FZ_NO_CORR")) no_corr_ = (nc[0] == '1');
+    if (const char* nd = getenv("FZ_NO_DYN_SCHED")) dyn_sched_ = !(nd[0] == '1');
+    sched_ctr_.alloc(64);
     if (gs_terms_ != 2) fused_ = false;
     if (const char* na = getenv("FZ_NO_AUX")) use_aux_ = !(na[0] == '1');
     if (const char* ng = getenv("FZ_NO_GRAPH")) use_graph_ = !(ng[0] == '1');
@@ -633,6 +655,7 @@ class Engine : public EngineBase {
     }
     ev_rel_.resize(rels_.size());
     for (auto& e : ev_rel_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_prep_, cudaEventDisableTiming));
     ev_rs_.resize(rels_.size());
     for (auto& e : ev_rs_) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ev_upd_.resize(types_.size());
@@ -787,8 +810,10 @@ class Engine : public EngineBase {
     if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_UNSUPPORTED, "piecewise products are for dfmf");
     begin_flags(st, centred_ && choose_single());
     if (!use_aux_) { grams(st, centred_); return; }
-    for (auto& tp : types_)
-      if (tp->need_gs) split(*tp, st, centred_);       // operand forms first: every streamed product needs them
+    if (!presplit_valid_)
+      for (auto& tp : types_)
+        if (tp->need_gs) split(*tp, st, centred_);     // operand forms first: every streamed product needs them
+    presplit_valid_ = false;
     begin_reductions(st);
   }
   bool gate_checks_next() const { return gate_enabled_ && (it_count_ < 4 || (it_count_ % 8) == 0); }
@@ -875,8 +900,10 @@ class Engine : public EngineBase {
       }
       theta_products(st);
     }
+    const bool presplit = dfmf && centred_ && use_aux_ && !no_presplit_ && (world_ == 1 || comm_) && tf_target_ < 0;
     for (size_t t = 0; t < types_.size(); ++t) {
       update_type((int)t, dfmf ? 1 : 0, st);
+      if (presplit && !comm_) CUDA_OK(cudaEventRecord(ev_upd_[t], st));
       if (comm_) {       // rows of the new factor go round while the next type updates (in-place all-gather)
         TypeRec& Tt = *types_[t];
         CUDA_OK(cudaEventRecord(ev_upd_[t], st));
@@ -886,6 +913,15 @@ class Engine : public EngineBase {
         CUDA_OK(cudaEventRecord(ev_gather_[t], comm_stream_));
         gather_pending_[t] = 1;
       }
+      if (presplit && types_[t]->need_gs) {     // next iteration's operand form of this type, beside the other types' updates
+        CUDA_OK(cudaStreamWaitEvent(aux_, comm_ ? ev_gather_[t] : ev_upd_[t], 0));
+        split(*types_[t], aux_, true, nxt(*types_[t]));
+      }
+    }
+    if (presplit) {
+      CUDA_OK(cudaEventRecord(ev_prep_, aux_));
+      CUDA_OK(cudaStreamWaitEvent(st, ev_prep_, 0));
+      presplit_valid_ = true;
     }
     for (auto& tp : types_) tp->cur ^= 1;
     CUDA_OK(cudaGetLastError());
@@ -915,6 +951,10 @@ class Engine : public EngineBase {
     }
     check_factors();
     other->check_factors();
+    // the pair's operand forms live side by side in one buffer (split_pair): no per-handle pre-splitting while paired
+    no_presplit_ = other->no_presplit_ = can_pair;
+    presplit_valid_ = other->presplit_valid_ = false;
+    struct Restore { Engine<T>*a, *b; ~Restore() { a->no_presplit_ = b->no_presplit_ = false; } } restore{this, other};
     for (int it = 0; it < n_iters; ++it) {
       const bool paired = can_pair && choose_single() && other->choose_single() && !gate_checks_next() && !other->gate_checks_next();
       if (!paired) {
@@ -1269,6 +1309,7 @@ class Engine : public EngineBase {
     CUDA_OK(cudaDeviceSynchronize());
     for (auto& rp : rels_) { rp->E.release(); rp->Es.release(); rp->Cx.release(); }
     for (auto& tp : types_) tp->has_factor = true;
+    presplit_valid_ = false;
   }
 
  private:
@@ -1330,15 +1371,16 @@ class Engine : public EngineBase {
   // tensor-core product of a bf16 relation with a split factor:  C (M x k) = op(R) * Gs[g_row0 + ., :]
   void umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g_row0, T* C, int64_t ldc, int M, int K, int k, cudaStream_t st);
 
-  void split(TypeRec& t, cudaStream_t st, bool centred = false) {
+  void split(TypeRec& t, cudaStream_t st, bool centred = false, const T* G = nullptr) {
+    if (G == nullptr) G = cur(t);
     const float* centre = nullptr;
     if (centred) {     // G = 1 c^T + D with c the column means; the bf16 terms represent D
-      col_sum_partial<T><<<t.centre_chunks, 256, 0, st>>>(cur(t), t.k, t.n, t.k, t.centre_rows_per_chunk, t.centre_part.template as<double>());
+      col_sum_partial<T><<<t.centre_chunks, 256, 0, st>>>(G, t.k, t.n, t.k, t.centre_rows_per_chunk, t.centre_part.template as<double>());
       finish_centre<<<1, 1024, 0, st>>>(t.centre_part.template as<double>(), t.centre_chunks, t.k, t.n, t.centre.template as<float>());
       launches += 2;
       centre = t.centre.template as<float>();
     }
-    split_factor<T><<<nblk(t.n_pad * kKp, 256), 256, 0, st>>>(cur(t), t.k, t.Gs.template as<__nv_bfloat16>(), t.n, t.n_pad, t.k, kKp,
+    split_factor<T><<<nblk(t.n_pad * kKp, 256), 256, 0, st>>>(G, t.k, t.Gs.template as<__nv_bfloat16>(), t.n, t.n_pad, t.k, kKp,
                                                                gs_terms_, centre);
     ++launches;
     t.hi_ptr = t.Gs.template as<__nv_bfloat16>();
@@ -1742,9 +1784,17 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
     q.n_rows = p.n_rows; q.n_cols = p.n_cols; q.k_a = p.k_a; q.k_b = p.k_b; q.gi_row0 = p.gi_row0;
     q.tma_flush = (r.has_tmB ? 1 : 0) | (r.has_tmA ? 2 : 0);
     q.probe = 0;
-    // persistent grid: one CTA per SM, each walking an equal share of the (row group x column tile) units
+    // persistent grid: one CTA per SM; three quarters of the (row group x column tile) units in equal static shares, the last
+    // quarter in chunks handed out on demand (umma_fused1.cuh: F1Segments)
     const long long units = (long long)pairs * tiles;
     const unsigned ctas = (unsigned)std::max<long long>(1, std::min<long long>(sm_count_, units));
+    q.dyn_chunk = 0;
+    q.work_counter = nullptr;
+    if (dyn_sched_ && units >= 16ll * ctas) {
+      q.dyn_chunk = (int)std::max<long long>(1, std::min<long long>(16, (units / 4) / (4ll * ctas)));
+      q.work_counter = sched_ctr_.template as<int>();
+      CUDA_OK(cudaMemsetAsync(q.work_counter, 0, sizeof(int), st));
+    }
     umma_fused1_kernel<<<ctas, kF1Threads, kF1SmemBytes, st>>>(r.tmX, Tj.tmG128, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX,
                                                                r.has_tmA ? r.tmA : r.tmX, q);
   } else if (fused_ver_ == 4 && r.v4_ok && !centred_) {
@@ -2290,6 +2340,21 @@ int fz_fill_uniform(void* dst, int dtype, int64_t ld, int64_t rows, int64_t cols
   if (dtype == FZ_BF16) fz::fill_hashed_uniform<__nv_bfloat16><<<g, 256, 0, st>>>((__nv_bfloat16*)dst, ld, rows, cols, row0, seed);
   else if (dtype == FZ_F32) fz::fill_hashed_uniform<float><<<g, 256, 0, st>>>((float*)dst, ld, rows, cols, row0, seed);
   else if (dtype == FZ_F64) fz::fill_hashed_uniform<double><<<g, 256, 0, st>>>((double*)dst, ld, rows, cols, row0, seed);
+  else return FZ_ERR_INVALID;
+  return cudaGetLastError() == cudaSuccess ? FZ_OK : FZ_ERR_CUDA;
+}
+
+int fz_unknown_mask(const void* data, int dtype, int64_t ld, int64_t rows, int64_t cols, uint8_t* mask, int64_t mask_ld, void* stream) {
+  if (!data || !mask || rows < 0 || cols < 0 || ld < cols || mask_ld < cols) return FZ_ERR_INVALID;
+  if (rows * cols == 0) return FZ_OK;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, data) != cudaSuccess || attr.type != cudaMemoryTypeDevice) return FZ_ERR_INVALID;
+  DeviceGuard guard(attr.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = fz::nblk(rows * cols, 256);
+  if (dtype == FZ_BF16) fz::unknown_mask<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)data, ld, rows, cols, mask, mask_ld);
+  else if (dtype == FZ_F32) fz::unknown_mask<float><<<g, 256, 0, st>>>((const float*)data, ld, rows, cols, mask, mask_ld);
+  else if (dtype == FZ_F64) fz::unknown_mask<double><<<g, 256, 0, st>>>((const double*)data, ld, rows, cols, mask, mask_ld);
   else return FZ_ERR_INVALID;
   return cudaGetLastError() == cudaSuccess ? FZ_OK : FZ_ERR_CUDA;
 }

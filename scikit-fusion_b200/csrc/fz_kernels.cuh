@@ -451,6 +451,17 @@ __global__ void finish_means(double* __restrict__ sum, const double* __restrict_
     sum[i] = (m == m) ? m : overall;
   }
 }
+// mask[r][c] = 1 where X[r][c] is not finite (NaN / +-inf), else 0: the completion mask of a device-resident relation
+// (the reference takes it from numpy masked arrays, decomposition/dfmc.py:69-94)
+template <class XT>
+__global__ void unknown_mask(const XT* __restrict__ X, long long ld, long long rows, long long cols, uint8_t* __restrict__ mask,
+                             long long mld) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols, c = idx % cols;
+  const double v = load_as<XT, double>(X + r * ld + c);
+  mask[r * mld + c] = (v == v && v - v == 0.0) ? 0 : 1;
+}
 // mode 0: every unknown <- scalar[0];  1: <- per_axis[row];  2: <- per_axis[col];  3: <- value
 template <class XT>
 __global__ void replace_unknown(XT* __restrict__ X, long long ld, long long rows, long long cols, int mode, const double* __restrict__ scalar,

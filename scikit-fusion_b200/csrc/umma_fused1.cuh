@@ -36,6 +36,8 @@ struct Fused1Params {
   int n_rows, n_cols;
   int k_a, k_b;
   int gi_row0;          // row of Gs_i that pairs with local row 0 of R (row-sharded factors)
+  int* work_counter;    // dynamic tail of the schedule: a device int, zero at launch (nullptr / dyn_chunk == 0: static only)
+  int dyn_chunk;        // units per dynamic chunk (0 = the whole launch is statically partitioned)
   int tma_flush;        // bit0: B partials go out as TMA reduce-add (needs tmB); bit1: A likewise (needs tmA); else red.global
   int probe;            // developer probe only (wrong results): bit0 no reductions, bit1 no B MMAs, bit2 no A MMAs
 };
@@ -51,22 +53,35 @@ constexpr int kF1StageBytes = 32768;                  // flush staging: 4 warps 
 constexpr int kF1SmemBytes = kF1RStages * kF1TileBytes + kF1GjSlots * kF1GBytes + kF1StageBytes + kF1Blocks * kF1GBytes + 1024 + 256;
 
 // Work of one launch = (row groups of 512 rows) x (128-column tiles), flattened row-group-major into "units" of one column
-// tile of one row group.  CTA b of a persistent grid owns the contiguous unit range [b U / G, (b + 1) U / G): every CTA
-// streams the same number of relation tiles (+-1 unit) whatever the shape -- no wave quantisation -- and a range is walked
-// as at most a few SEGMENTS (maximal runs inside one row group), each with its own resident Gs_i and A accumulators.
+// tile of one row group.  The first three quarters of the units are partitioned STATICALLY: CTA b of the persistent grid owns
+// a contiguous range, walked as at most a few SEGMENTS (maximal runs inside one row group, each with its own resident Gs_i
+// and A accumulators) -- no wave quantisation, no per-unit overhead.  The last quarter is handed out DYNAMICALLY in small
+// chunks (an atomic counter; the relation-producer warp fetches, the other roles follow through a shared-memory ring), so an
+// SM that shares its cycles with another kernel -- the fp64 reductions of the previous relation, an NCCL reduce-scatter --
+// simply takes fewer chunks instead of holding the whole launch back.
 struct F1Segments {
-  long long u, u_end;
-  int tiles;
-  __device__ F1Segments(int n_rows, int n_cols) {
+  long long u, u_end, units, dyn_begin;
+  int tiles, chunk, fetched;
+  __device__ F1Segments(int n_rows, int n_cols, int dyn_chunk) {
     tiles = (n_cols + kF1Tile - 1) / kF1Tile;
     const long long groups = (n_rows + kF1Blocks * kF1Tile - 1) / (kF1Blocks * kF1Tile);
-    const long long units = groups * tiles;
-    u = units * blockIdx.x / gridDim.x;
-    u_end = units * (blockIdx.x + 1) / gridDim.x;
+    units = groups * tiles;
+    chunk = dyn_chunk;
+    fetched = 0;
+    dyn_begin = chunk > 0 ? units - units / 4 : units;
+    u = dyn_begin * blockIdx.x / gridDim.x;
+    u_end = dyn_begin * (blockIdx.x + 1) / gridDim.x;
   }
-  // next segment: row group, first tile, number of tiles
-  __device__ bool next(int& group, int& tile0, int& n) {
-    if (u >= u_end) return false;
+  // next segment: row group, first tile, number of tiles.  fetch(k) returns the k-th dynamic chunk index of this CTA.
+  template <class Fetch>
+  __device__ bool next(int& group, int& tile0, int& n, Fetch&& fetch) {
+    while (u >= u_end) {
+      if (chunk <= 0) return false;
+      const long long c = fetch(fetched++);
+      u = dyn_begin + c * chunk;
+      u_end = min(units, u + chunk);
+      if (u >= units) { chunk = 0; return false; }
+    }
     group = (int)(u / tiles);
     tile0 = (int)(u % tiles);
     n = (int)min((long long)(tiles - tile0), u_end - u);
@@ -99,7 +114,10 @@ umma_fused1_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16
   uint64_t* gi_empty = gi_full + 1;            // [1]  per segment: the segment's B-product MMAs have read Gs_i
   uint64_t* aacc_full = gi_empty + 1;          // [1]  per segment
   uint64_t* aacc_empty = aacc_full + 1;        // [1]  per segment: the epilogue has drained A_acc
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aacc_empty + 1);
+  uint64_t* q_full = aacc_empty + 1;           // [4]  dynamic-chunk ring: entry published by the relation producer
+  uint64_t* q_empty = q_full + 4;              // [4]  ... and read by the MMA warp, the Gs producer and the 4 epilogue warps
+  int* q_val = reinterpret_cast<int*>(q_empty + 4);   // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_val + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,6 +138,7 @@ umma_fused1_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16
     ptx::mbar_init(gi_empty, 1);
     ptx::mbar_init(aacc_full, 1);
     ptx::mbar_init(aacc_empty, 128);
+    for (int s = 0; s < 4; ++s) { ptx::mbar_init(&q_full[s], 1); ptx::mbar_init(&q_empty[s], 6); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -127,15 +146,35 @@ umma_fused1_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  F1Segments segs(p.n_rows, p.n_cols);
+  F1Segments segs(p.n_rows, p.n_cols, p.work_counter != nullptr ? p.dyn_chunk : 0);
   int group, tile0, n_tiles;
+  // k-th dynamic chunk of this CTA: fetched from the global counter by the relation producer, followed by everyone else
+  auto fetch_lead = [&](int k) -> long long {
+    const int slot = k & 3;
+    ptx::mbar_wait(&q_empty[slot], ((k >> 2) & 1) ^ 1);
+    if (ptx::elect_one()) {
+      q_val[slot] = atomicAdd(p.work_counter, 1);
+      ptx::mbar_arrive(&q_full[slot]);
+    }
+    __syncwarp();
+    return (long long)q_val[slot];
+  };
+  auto fetch_follow = [&](int k) -> long long {
+    const int slot = k & 3;
+    ptx::mbar_wait(&q_full[slot], (k >> 2) & 1);
+    const int v = q_val[slot];
+    __syncwarp();
+    if (ptx::elect_one()) ptx::mbar_arrive(&q_empty[slot]);
+    __syncwarp();
+    return (long long)v;
+  };
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer: relation tiles
     // (whole warp, one elected lane issues: a divergent `if (lane == 0)` makes ptxas wrap every TMA / tcgen05
     //  instruction in a ~100-cycle waterfall loop, csrc/dev/mma_pace.cu)
     int it = 0;
-    while (segs.next(group, tile0, n_tiles)) {
+    while (segs.next(group, tile0, n_tiles, fetch_lead)) {
       const int r0 = group * kF1Blocks * kF1Tile;
       const int nb = min(kF1Blocks, (p.n_rows - r0 + kF1Tile - 1) / kF1Tile);
       for (int c = 0; c < n_tiles; ++c) {
@@ -156,7 +195,7 @@ umma_fused1_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16
   } else if (warp == 6) {
     // ---------------------------------------------------------------- TMA producer: factor operands
     int ct = 0, seg = 0;
-    while (segs.next(group, tile0, n_tiles)) {
+    while (segs.next(group, tile0, n_tiles, fetch_follow)) {
       const int r0 = group * kF1Blocks * kF1Tile;
       const int nb = min(kF1Blocks, (p.n_rows - r0 + kF1Tile - 1) / kF1Tile);
       ptx::mbar_wait(gi_empty, (seg & 1) ^ 1);                     // previous segment's MMAs are done with Gs_i
@@ -184,7 +223,7 @@ umma_fused1_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16
     const bool do_a = !(p.probe & 4), do_b = !(p.probe & 2);
     const uint32_t r_base = ptx::smem_u32(r_st), gj_base = ptx::smem_u32(gj_st), gi_base = ptx::smem_u32(gi_st);
     int it = 0, ct = 0, seg = 0;
-    while (segs.next(group, tile0, n_tiles)) {
+    while (segs.next(group, tile0, n_tiles, fetch_follow)) {
       const int r0 = group * kF1Blocks * kF1Tile;
       const int nb = min(kF1Blocks, (p.n_rows - r0 + kF1Tile - 1) / kF1Tile);
       ptx::mbar_wait(aacc_empty, (seg & 1) ^ 1);                   // the previous segment's A accumulators are drained
@@ -243,7 +282,7 @@ umma_fused1_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16
     const bool b_tma = (p.tma_flush & 1) != 0, a_tma = (p.tma_flush & 2) != 0;
     bool staged = false;                                          // this warp has reduces in flight that read its staging
     int ct = 0, seg = 0;
-    while (segs.next(group, tile0, n_tiles)) {
+    while (segs.next(group, tile0, n_tiles, fetch_follow)) {
       const int r0 = group * kF1Blocks * kF1Tile;
       const int nb = min(kF1Blocks, (p.n_rows - r0 + kF1Tile - 1) / kF1Tile);
       for (int c = 0; c < n_tiles; ++c, ++ct) {

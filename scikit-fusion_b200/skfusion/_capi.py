@@ -27,7 +27,7 @@ SYMBOLS = [
     "fz_phase_products", "fz_phase_update", "fz_phase_products_begin", "fz_phase_product_relation", "fz_phase_products_end", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
     "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete", "fz_profile_product",
     "fz_fill_uniform", "fz_profile", "fz_profile_read",
-    "fz_init_fill", "fz_relation_norms", "fz_init_add_sampled_means", "fz_init_end", "fz_fill_unknown",
+    "fz_init_fill", "fz_relation_norms", "fz_init_add_sampled_means", "fz_init_end", "fz_fill_unknown", "fz_unknown_mask",
 ]
 
 
@@ -118,6 +118,7 @@ def lib():
         "fz_init_add_sampled_means": (i32, [vp, i32, i32, ctypes.POINTER(ctypes.c_int32), i32, vp]),
         "fz_init_end": (i32, [vp]),
         "fz_fill_unknown": (i32, [vp, i32, i64, i64, i64, i32, ctypes.c_double, vp]),
+        "fz_unknown_mask": (i32, [vp, i32, i64, i64, i64, vp, i64, vp]),
         "fz_profile": (i32, [vp, i32]),
         "fz_profile_read": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(ctypes.c_double)]),
@@ -209,6 +210,20 @@ def fill_unknown(tensor, mode, value=0.0, stream=0):
     if rc != 0:
         raise EngineError("fz_fill_unknown failed (%d)" % rc)
     return tensor
+
+
+def unknown_mask(tensor, stream=0):
+    """uint8 torch CUDA tensor, 1 where the 2-D torch CUDA tensor holds a non-finite entry (see fz_unknown_mask)."""
+    import torch
+    if not _is_torch_cuda(tensor) or tensor.dim() != 2 or tensor.stride(1) != 1:
+        raise ValueError("unknown_mask needs a 2-D torch CUDA tensor with unit inner stride")
+    mask = torch.empty(tuple(tensor.shape), dtype=torch.uint8, device=tensor.device)
+    rc = lib().fz_unknown_mask(ctypes.c_void_p(tensor.data_ptr()), dtype_code(str(tensor.dtype)), int(tensor.stride(0)),
+                               int(tensor.shape[0]), int(tensor.shape[1]), ctypes.c_void_p(mask.data_ptr()), int(mask.stride(0)),
+                               ctypes.c_void_p(stream))
+    if rc != 0:
+        raise EngineError("fz_unknown_mask failed (%d)" % rc)
+    return mask
 
 
 def _is_torch_cuda(x):

@@ -165,10 +165,17 @@ def _blocks_for_fit(graph, with_masks):
     R, T, M = {}, {}, {}
     for row_type, col_type in product(graph.object_types, repeat=2):
         for relation in graph.get_relations(row_type, col_type):
+            mask = None
+            if with_masks and _capi._is_torch_cuda(relation.data) and relation.row_type != relation.col_type:
+                # device-resident relation: its unknown (non-finite) entries are the completion mask, taken on the GPU before
+                # the fill.  Like numpy's masked arrays upstream, the mask survives the 'mean' / constant fills and is dropped
+                # by 'row_mean' / 'col_mean' (what filled() returns there is a plain array).
+                if relation.fill_value not in ("row_mean", "col_mean"):
+                    found = _capi.unknown_mask(relation.data)
+                    mask = found if bool(found.any().item()) else None
             data = relation.filled()
             if relation.preprocessor:
                 data = relation.preprocessor(data)
-            mask = None
             if np.ma.is_masked(data):
                 mask = data.mask
                 data = data.data
