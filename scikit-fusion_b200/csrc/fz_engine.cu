@@ -322,7 +322,9 @@ class Engine : public EngineBase {
   int terms_ = 2;           // split terms of the factor operand: 1..3 plain form; FZ_TERMS_AUTO / FZ_TERMS_CENTRED1: centred form
   int gs_terms_ = 2;        // terms stored in Gs (the centred forms always keep [hi | lo])
   bool centred_ = false;    // mean-centred operand form for the fused dfmf products (terms_ <= 0)
-  bool dyn_sched_ = true;   // FZ_NO_DYN_SCHED=1: the single-term kernel's launch is partitioned statically only
+  int dyn_sched_ = -1;      // dynamic tail of the single-term kernel's schedule: -1 = when the handle shares the GPU with its own
+                            // collectives (sharded + fz_comm_init; alone on the GPU the tail costs ~4 % and buys nothing:
+                            // profiles/r02_fused1_probe_hybrid_schedule.log), FZ_DYN_SCHED=0|1 overrides
   DevBuf sched_ctr_;        // chunk counter of its dynamic tail
   bool no_corr_ = false;    // FZ_NO_CORR=1 (studies / tests only): single-term kernel WITHOUT the first-order correction of M
   bool single_now_ = false; // this iteration's fused products use the single-term kernel (umma_fused1.cuh) + M correction
@@ -638,7 +640,7 @@ class Engine : public EngineBase {
     err_acc_.alloc(8);
     if (const char* cs = getenv("FZ_FUSED_CSPLIT")) fused_csplit_ = atoi(cs);
     if (const char* nc = getenv("FZ_NO_CORR")) no_corr_ = (nc[0] == '1');
-    if (const char* nd = getenv("FZ_NO_DYN_SCHED")) dyn_sched_ = !(nd[0] == '1');
+    if (const char* nd = getenv("FZ_DYN_SCHED")) dyn_sched_ = (nd[0] == '1') ? 1 : 0;
     sched_ctr_.alloc(64);
     if (gs_terms_ != 2) fused_ = false;
     if (const char* na = getenv("FZ_NO_AUX")) use_aux_ = !(na[0] == '1');
@@ -739,9 +741,21 @@ class Engine : public EngineBase {
   // r's B partial runs under the streamed products of relation r+1, the Gram all-reduce and the pseudo-inverses under the
   // first products, the all-gather of type t's new factor under the update of type t+1.
   void run_one_sharded(int algo, cudaStream_t st) {
-    if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_UNSUPPORTED, "sharded handles run dfmf (dfmc and transform are replicas)");
     const NcclApi& nc = nccl_api();
     const ncclDataType_t dt = (kDT == FZ_F32) ? ncclFloat32 : ncclFloat64;
+    if (algo == FZ_DFMC) {
+      // completion: the imputation R[M] <- (G_i S G_j^T)[M] is row-local (rows of R and G_i local, G_j whole), so dfmc shards
+      // like dfmf; its B partials can only be exchanged after the imputation, inside phase_update (_dfmc.py:319-345)
+      phase_products(algo, st);
+      CUDA_OK(cudaEventRecord(ev_c0_, st));
+      CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
+      NCCL_OK(nc.AllReduce(small_.p, small_.p, (size_t)small_count_, ncclFloat64, ncclSum, comm_, comm_stream_));
+      CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
+      CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));
+      phase_update(algo, st);
+      return;
+    }
+    if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_INVALID, "unknown algorithm");
     phase_products_begin(algo, st);
     for (size_t r = 0; r < rels_.size(); ++r) {
       phase_product_relation(algo, (int)r, st);
@@ -782,7 +796,8 @@ class Engine : public EngineBase {
     need_final();
     check_factors();
     if (algo == FZ_DFMC) {
-      if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "dfmc is single-GPU in this round");
+      if (world_ != 1 && !comm_) FZ_THROW(FZ_ERR_UNSUPPORTED, "dfmc on a sharded handle needs fz_comm_init");
+      wait_gathers(st);
       if (!dfmc_started_) {
         for (auto& rp : rels_)                                   // _dfmc.py:287-292
           if (rp->mask) {
@@ -887,7 +902,7 @@ class Engine : public EngineBase {
         TypeRec& Ti = *types_[r.ti];
         TypeRec& Tj = *types_[r.tj];
         ensure_T1(r);
-        gemm(cur(Ti), Ti.k, r.W4.template as<T>(), Tj.k, r.T1.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, Ti.k, false, st);
+        gemm(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.W4.template as<T>(), Tj.k, r.T1.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, Ti.k, false, st);
         dim3 g(nblk(r.cols, 32), nblk(r.rows_loc, 32));
         impute_masked<T><<<g, 256, 0, st>>>((T*)r.data, r.ld, r.mask, r.mask_ld, r.T1.template as<T>(), Tj.k, cur(Tj), Tj.k,
                                             r.rows_loc, r.cols, Tj.k);
@@ -897,6 +912,17 @@ class Engine : public EngineBase {
         if (rp->theta) continue;
         if (rp->mask) product_A(*rp, st);   // only completed relations changed
         product_B(*rp, st);
+      }
+      if (comm_) {      // the B partials of the completed relations go to the rows' owners before the update reads them
+        CUDA_OK(cudaEventRecord(ev_c0_, st));
+        CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
+        for (auto& rp : rels_) {
+          if (rp->theta) continue;
+          NCCL_OK(nccl_api().ReduceScatter(rp->B.p, rp->Bloc.p, (size_t)types_[rp->tj]->m_loc * types_[rp->ti]->k,
+                                           (kDT == FZ_F32) ? ncclFloat32 : ncclFloat64, ncclSum, comm_, comm_stream_));
+        }
+        CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
+        CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));
       }
       theta_products(st);
     }
@@ -1790,7 +1816,7 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
     const unsigned ctas = (unsigned)std::max<long long>(1, std::min<long long>(sm_count_, units));
     q.dyn_chunk = 0;
     q.work_counter = nullptr;
-    if (dyn_sched_ && units >= 16ll * ctas) {
+    if ((dyn_sched_ == 1 || (dyn_sched_ < 0 && comm_ != nullptr)) && units >= 16ll * ctas) {
       q.dyn_chunk = (int)std::max<long long>(1, std::min<long long>(16, (units / 4) / (4ll * ctas)));
       q.work_counter = sched_ctr_.template as<int>();
       CUDA_OK(cudaMemsetAsync(q.work_counter, 0, sizeof(int), st));

@@ -218,13 +218,11 @@ def _row_block(mat, lo, hi, device):
 
 def _fit_sharded(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_type, stopping, stopping_system, compute_err,
                  callback, random_state, opts):
-    """dfmf over n_gpus GPUs of this box from ONE process (reference entry: Dfmf.fuse -> dfmf(), dfmf.py:55-106): rank p's
+    """dfmf / dfmc over n_gpus GPUs of this box from ONE process (reference entry: Dfmf.fuse -> dfmf(), dfmf.py:55-106): rank p's
     handle lives on device p and holds the row blocks [lo_p, hi_p) of every relation; the handles form one shard group and the
     library runs one host thread per handle with NCCL for the three exchanges (include/fz_fusion.h: fz_group_*).  Objective,
     early stopping and the callback work as on one GPU; results are read from rank 0 (every rank holds the whole factors)."""
     from .distributed import local_rows
-    if algo != _capi.FZ_DFMF:
-        raise ValueError("n_gpus > 1 is for Dfmf; Dfmc re-imputes whole relations every iteration and runs on one GPU")
     world = int(opts["n_gpus"])
     base = int(opts["device"])
     sizes = count_objects(obj_types, R)
@@ -241,7 +239,11 @@ def _fit_sharded(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_typ
             prob.add_types(obj_types, sizes, obj_type2rank)
             block = lambda blocks: {key: [_row_block(mat, *local_rows(sizes[key[0]], world, p), base + p) for mat in mats]
                                     for key, mats in blocks.items()}
-            prob.add_blocks(block(R), block(Theta), None)
+            masks = None
+            if M is not None:       # completion masks shard with their relations' rows (the imputation is row-local)
+                masks = {key: [None if m is None else _row_block(m, *local_rows(sizes[key[0]], world, p), base + p) for m in ms]
+                         for key, ms in M.items()}
+            prob.add_blocks(block(R), block(Theta), masks)
             for t in obj_types:
                 prob.engine.set_factor(prob.type_id[t], G0[t, t])
             prob.engine.finalize()

@@ -75,3 +75,21 @@ def test_estimator_keyword_n_gpus():
     one = fusion.Dfmf(max_iter=12, init_type="random", random_state=5, dtype="float64").fuse(graph)
     two = fusion.Dfmf(max_iter=12, init_type="random", random_state=5, dtype="float64", n_gpus=2).fuse(graph)
     assert rel_fro(one.factor(t1), two.factor(t1)) < 1e-10 and rel_fro(one.backbone(rel), two.backbone(rel)) < 1e-10
+
+
+def test_completion_on_two_gpus_equals_the_oracle():
+    """Dfmc shards like Dfmf: the imputation of the masked entries is local to the rows a rank holds."""
+    if _gpus() < 2:
+        pytest.skip("needs two GPUs")
+    from skfusion.fusion import solver
+    rs = np.random.RandomState(2)
+    types, ranks = ["u", "m", "g"], {"u": 7, "m": 9, "g": 3}
+    R = {("u", "m"): [rs.rand(81, 64)], ("m", "g"): [rs.rand(64, 11)]}
+    M = {("u", "m"): [rs.rand(81, 64) < 0.3], ("m", "g"): [None]}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Go, So = oracle.dfmc(R, M, {}, types, ranks, max_iter=12, init_type="random", random_state=np.random.RandomState(4))
+        G, S = solver.dfmc(R, M, {}, types, ranks, max_iter=12, init_type="random", random_state=np.random.RandomState(4),
+                           dtype="float64", n_gpus=2)
+    assert max(rel_fro(Go[t, t], G[t, t]) for t in types) < 1e-8
+    assert max(rel_fro(So[k][0], S[k][0]) for k in So) < 1e-7
