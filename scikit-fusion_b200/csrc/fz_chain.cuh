@@ -341,6 +341,46 @@ backbone_chain(const BackboneJob<T>* __restrict__ jobs) {
   }
 }
 
+// Squared Frobenius residual of one relation from k x k quantities only (reference objective, _dfmf.py:306-319, without
+// forming the n_i x n_j reconstruction):
+//     ||R - G_i S G_j^T||_F^2 = ||R||_F^2 - 2 tr(S^T (G_i^T R G_j)) + tr(S^T (G_i^T G_i) S (G_j^T G_j))
+// with M = G_i^T R G_j and the Gram matrices of the CURRENT factors (the raw sums the products phase leaves in the all-reduce
+// buffer -- on a sharded handle they are already summed over the ranks).  One CTA per relation, fp64.
+struct TraceJob {
+  const double* M;        // k_i x k_j
+  const double* gram_i;   // k_i x k_i
+  const double* gram_j;   // k_j x k_j
+  const double* S;        // k_i x k_j
+  const double* rnorm2;   // [1]  ||R||_F^2
+  double* work;           // 2 * max(k_i, k_j)^2
+  double* out;            // [1]
+  int ki, kj;
+};
+__global__ void __launch_bounds__(kChainThreads)
+trace_objective(const TraceJob* __restrict__ jobs) {
+  const TraceJob job = jobs[blockIdx.x];
+  const int ki = job.ki, kj = job.kj, tid = threadIdx.x, nth = blockDim.x;
+  const int km = max(ki, kj);
+  double* U = job.work;
+  double* V = job.work + (long long)km * km;
+  extern __shared__ double chain_stage[];
+  double* stage = (km <= kChainSmemDim) ? chain_stage : nullptr;
+  block_mm(U, kj, job.gram_i, ki, false, job.S, kj, false, ki, kj, ki, stage);      // U = Gram_i S
+  __syncthreads();
+  block_mm(V, kj, U, kj, false, job.gram_j, kj, false, ki, kj, kj, stage);          // V = U Gram_j
+  __syncthreads();
+  __shared__ double red[kChainThreads];
+  double acc = 0.0;
+  for (int o = tid; o < ki * kj; o += nth) acc += job.S[o] * (V[o] - 2.0 * job.M[o]);
+  red[tid] = acc;
+  __syncthreads();
+  for (int w = nth >> 1; w > 0; w >>= 1) {
+    if (tid < w) red[tid] += red[tid + w];
+    __syncthreads();
+  }
+  if (tid == 0) job.out[0] = job.rnorm2[0] + red[0];
+}
+
 template <class T>
 struct TypeSumJob {
   const double* const* mats;  // n_mats pointers to k x k matrices (t2 of row-role relations, t5 of column-role ones)

@@ -73,7 +73,7 @@ struct DevBuf {
   void alloc(size_t n, bool zero = true) {
     if (n == 0) n = 16;
     if (p && bytes == n) {   // same size again (e.g. a second fz_transform_prepare): keep the allocation
-      if (zero) CUDA_OK(cudaMemset(p, 0, n));
+      if (zero) zero_now(n);
       return;
     }
     release();
@@ -83,7 +83,13 @@ struct DevBuf {
       FZ_THROW(FZ_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
     }
     bytes = n;
-    if (zero) CUDA_OK(cudaMemset(p, 0, n));
+    if (zero) zero_now(n);
+  }
+  // Zeroing runs on the legacy default stream, which non-blocking caller streams do not wait for: finish it here, so that
+  // whatever stream the caller enqueues on next finds the buffer cleared (allocation is a set-up step, never in the loop).
+  void zero_now(size_t n) {
+    CUDA_OK(cudaMemset(p, 0, n));
+    CUDA_OK(cudaStreamSynchronize(nullptr));
   }
   template <class U> U* as() const { return reinterpret_cast<U*>(p); }
 };
@@ -298,6 +304,7 @@ class Engine : public EngineBase {
     bool has_backbone = false;
     CUtensorMap tmX, tmXT, tmEs, tmB, tmA;
     bool has_tmB = false, has_tmA = false;
+    DevBuf colsum_loc;           // sharded with a communicator: this rank's share of the column sums (colsum then holds the total)
     DevBuf rowsum, colsum;       // centred operand form: row / column sums of the stored relation (fp32), computed once
     bool sums_ready = false;
     int corr_chunks = 0, corr_rows_per_chunk = 0;   // first-order correction of M (single-term form): extra slots of M_part
@@ -318,13 +325,21 @@ class Engine : public EngineBase {
   // operand forms of the NEXT iteration are built per type right behind that type's update (and all-gather), beside the
   // updates of the other types, instead of in front of the next iteration's first product
   bool presplit_valid_ = false, no_presplit_ = false;
+  // the products of the CURRENT factors are already in the buffers (fz_objective ran them for its trace form): the next
+  // iteration starts from them instead of streaming the relations again
+  bool products_valid_ = false;
+  bool obj_exact_ = false;      // FZ_OBJ_EXACT=1: always the n_i x n_j form of the objective
+  DevBuf rnorm2_, trace_jobs_, trace_out_;
+  bool rnorm2_ready_ = false;
   cudaEvent_t ev_prep_ = nullptr;
   int terms_ = 2;           // split terms of the factor operand: 1..3 plain form; FZ_TERMS_AUTO / FZ_TERMS_CENTRED1: centred form
   int gs_terms_ = 2;        // terms stored in Gs (the centred forms always keep [hi | lo])
   bool centred_ = false;    // mean-centred operand form for the fused dfmf products (terms_ <= 0)
-  int dyn_sched_ = -1;      // dynamic tail of the single-term kernel's schedule: -1 = when the handle shares the GPU with its own
-                            // collectives (sharded + fz_comm_init; alone on the GPU the tail costs ~4 % and buys nothing:
-                            // profiles/r02_fused1_probe_hybrid_schedule.log), FZ_DYN_SCHED=0|1 overrides
+  bool dmma_ = true;        // fp64 Gram / G_i^T A reductions on the fp64 tensor cores (FZ_NO_DMMA=1: CUDA-core kernel)
+  int dyn_sched_ = 0;       // dynamic tail of the single-term kernel's schedule (FZ_DYN_SCHED=1).  Off by default: alone on the GPU
+                            // the tail costs ~4 % (profiles/r02_fused1_probe_hybrid_schedule.log); beside NCCL at 4 GPUs the kernel
+                            // itself gets faster (0.69 -> 0.73 of the roofline) but the step does not -- the work it was sharing
+                            // the SMs with still has to run (profiles/r02_bench_n4_{static,dynamic_tail}.log)
   DevBuf sched_ctr_;        // chunk counter of its dynamic tail
   bool no_corr_ = false;    // FZ_NO_CORR=1 (studies / tests only): single-term kernel WITHOUT the first-order correction of M
   bool single_now_ = false; // this iteration's fused products use the single-term kernel (umma_fused1.cuh) + M correction
@@ -501,6 +516,7 @@ class Engine : public EngineBase {
     CUDA_OK(cudaStreamSynchronize(0));
     Tt.has_factor = true;
     presplit_valid_ = false;
+    products_valid_ = false;
   }
 
   void set_backbone(int rel, const void* S, int64_t ld, int src, int mem) override {
@@ -640,6 +656,8 @@ class Engine : public EngineBase {
     err_acc_.alloc(8);
     if (const char* cs = getenv("FZ_FUSED_CSPLIT")) fused_csplit_ = atoi(cs);
     if (const char* nc = getenv("FZ_NO_CORR")) no_corr_ = (nc[0] == '1');
+    if (const char* nm = getenv("FZ_NO_DMMA")) dmma_ = !(nm[0] == '1');
+    if (const char* oe = getenv("FZ_OBJ_EXACT")) obj_exact_ = (oe[0] == '1');
     if (const char* nd = getenv("FZ_DYN_SCHED")) dyn_sched_ = (nd[0] == '1') ? 1 : 0;
     sched_ctr_.alloc(64);
     if (gs_terms_ != 2) fused_ = false;
@@ -734,7 +752,8 @@ class Engine : public EngineBase {
   }
 
   void run_one(int algo, cudaStream_t st) {
-    phase_products(algo, st);
+    if (!(products_valid_ && algo == FZ_DFMF)) phase_products(algo, st);
+    products_valid_ = false;
     phase_update(algo, st);
   }
   // One sharded iteration with the collectives on the communicator's stream: the reduce-scatter of relation
@@ -756,6 +775,14 @@ class Engine : public EngineBase {
       return;
     }
     if (algo != FZ_DFMF) FZ_THROW(FZ_ERR_INVALID, "unknown algorithm");
+    if (!products_valid_) sharded_products(st);
+    products_valid_ = false;
+    phase_update(algo, st);
+  }
+  void sharded_products(cudaStream_t st) {
+    const int algo = FZ_DFMF;
+    const NcclApi& nc = nccl_api();
+    const ncclDataType_t dt = (kDT == FZ_F32) ? ncclFloat32 : ncclFloat64;
     phase_products_begin(algo, st);
     for (size_t r = 0; r < rels_.size(); ++r) {
       phase_product_relation(algo, (int)r, st);
@@ -763,6 +790,7 @@ class Engine : public EngineBase {
       if (rel.theta) continue;
       CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_rel_[r], 0));            // this relation's B partial is complete
       NCCL_OK(nc.ReduceScatter(rel.B.p, rel.Bloc.p, (size_t)types_[rel.tj]->m_loc * types_[rel.ti]->k, dt, ncclSum, comm_, comm_stream_));
+      if (centred_ && rel.storage == FZ_BF16) rank1_add_local(rel, comm_stream_);
       if (corr_deferred()) {      // the correction of M reads this rank's reduce-scattered rows of B
         cudaStream_t fin = use_aux_ ? aux_ : st;
         CUDA_OK(cudaEventRecord(ev_rs_[r], comm_stream_));
@@ -779,7 +807,6 @@ class Engine : public EngineBase {
                            ncclFloat64, ncclSum, comm_, comm_stream_));
     CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
     CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));                           // every reduce-scatter and the all-reduce have landed
-    phase_update(algo, st);
   }
   void wait_gathers(cudaStream_t st) {
     for (size_t t = 0; t < gather_pending_.size(); ++t)
@@ -862,6 +889,7 @@ class Engine : public EngineBase {
     (void)algo;
     RelRec& r = relation(rel);
     if (r.theta) return;
+    if (centred_ && comm_ && r.storage == FZ_BF16) ensure_sums(r, st);     // holds a collective: every rank, rows or not
     if (!product_AB_fused(r, st)) {
       product_A(r, st);
       product_B(r, st);
@@ -980,6 +1008,7 @@ class Engine : public EngineBase {
     // the pair's operand forms live side by side in one buffer (split_pair): no per-handle pre-splitting while paired
     no_presplit_ = other->no_presplit_ = can_pair;
     presplit_valid_ = other->presplit_valid_ = false;
+    products_valid_ = other->products_valid_ = false;
     struct Restore { Engine<T>*a, *b; ~Restore() { a->no_presplit_ = b->no_presplit_ = false; } } restore{this, other};
     for (int it = 0; it < n_iters; ++it) {
       const bool paired = can_pair && choose_single() && other->choose_single() && !gate_checks_next() && !other->gate_checks_next();
@@ -1149,6 +1178,7 @@ class Engine : public EngineBase {
     int n_rel = 0;
     for (auto& rp : rels_) n_rel += rp->theta ? 0 : 1;
     if (n_rel == 0) { if (total) *total = 0.0; return; }
+    if (objective_trace(per_rel, total, n_rel, st)) return;
     err_acc_.alloc((size_t)n_rel * 8, false);
     CUDA_OK(cudaMemsetAsync(err_acc_.p, 0, (size_t)n_rel * 8, st));
     int idx = 0;
@@ -1188,6 +1218,88 @@ class Engine : public EngineBase {
       sum += e;
     }
     if (total) *total = sum;
+  }
+
+  // The objective without the n_i x n_j pass: run the products of the CURRENT factors -- the very work the
+  // next iteration starts with, which then skips it -- and evaluate ||R||^2 - 2 tr(S^T M) + tr(S^T Gram_i S Gram_j) per
+  // relation in fp64.  dfmf handles only (dfmc rewrites R; transform has no live products).  Returns false -- the caller then
+  // takes the exact n^2 form -- when the form does not apply or when a residual is so small against ||R|| (< 10 %) that the
+  // difference of large numbers would lose it.
+  bool objective_trace(double* per_rel, double* total, int n_rel, cudaStream_t st) {
+    if (obj_exact_ || tf_target_ >= 0 || dfmc_started_ || it_count_ == 0) return false;
+    for (auto& rp : rels_)
+      if (rp->mask != nullptr) return false;
+    if (!rnorm2_ready_) {
+      rnorm2_.alloc((size_t)n_rel * 8);
+      int idx = 0;
+      for (auto& rp : rels_) {
+        RelRec& r = *rp;
+        if (r.theta) continue;
+        double* dst = rnorm2_.template as<double>() + idx++;
+        if (r.rows_loc <= 0) continue;
+        const int chunks = (int)std::min<int64_t>(128, std::max<int64_t>(1, (r.rows_loc + 127) / 128));
+        const int64_t rpc = (r.rows_loc + chunks - 1) / chunks;
+        DevBuf part;
+        part.alloc((size_t)chunks * r.cols * 8, false);
+        dim3 g(nblk(r.cols, 256), chunks);
+        if (r.storage == FZ_BF16) col_sumsq_partial<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, rpc, part.template as<double>());
+        else col_sumsq_partial<T><<<g, 256, 0, st>>>((const T*)r.data, r.ld, r.rows_loc, r.cols, rpc, part.template as<double>());
+        total_sum<<<1, 1024, 0, st>>>(part.template as<double>(), (long long)chunks * r.cols, dst);
+        launches += 2;
+        CUDA_OK(cudaStreamSynchronize(st));
+      }
+      if (comm_) {
+        CUDA_OK(cudaEventRecord(ev_c0_, st));
+        CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
+        NCCL_OK(nccl_api().AllReduce(rnorm2_.p, rnorm2_.p, (size_t)n_rel, ncclFloat64, ncclSum, comm_, comm_stream_));
+        CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
+        CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));
+      }
+      std::vector<TraceJob> jobs;
+      trace_out_.alloc((size_t)n_rel * 8);
+      idx = 0;
+      for (auto& rp : rels_) {
+        RelRec& r = *rp;
+        if (r.theta) continue;
+        TraceJob j;
+        j.M = r.M_raw;
+        j.gram_i = types_[r.ti]->gram_raw;
+        j.gram_j = types_[r.tj]->gram_raw;
+        j.S = r.S.template as<double>();
+        j.rnorm2 = rnorm2_.template as<double>() + idx;
+        j.work = r.work.template as<double>();
+        j.out = trace_out_.template as<double>() + idx;
+        j.ki = types_[r.ti]->k;
+        j.kj = types_[r.tj]->k;
+        jobs.push_back(j);
+        ++idx;
+      }
+      trace_jobs_.alloc(jobs.size() * sizeof(TraceJob), false);
+      CUDA_OK(cudaMemcpy(trace_jobs_.p, jobs.data(), jobs.size() * sizeof(TraceJob), cudaMemcpyHostToDevice));
+      rnorm2_ready_ = true;
+    }
+    if (!products_valid_) {
+      if (world_ != 1) sharded_products(st);
+      else phase_products(FZ_DFMF, st);
+      products_valid_ = true;
+    }
+    trace_objective<<<(unsigned)n_rel, kChainThreads, kChainSmemBytes, st>>>(trace_jobs_.template as<TraceJob>());
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    std::vector<double> sq((size_t)n_rel), rn((size_t)n_rel);
+    CUDA_OK(cudaMemcpyAsync(sq.data(), trace_out_.p, (size_t)n_rel * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(rn.data(), rnorm2_.p, (size_t)n_rel * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_rel; ++i)
+      if (!(sq[i] >= 1e-2 * rn[i])) return false;     // residual below 10 % of ||R|| (or not a number): take the exact form
+    double sum = 0.0;
+    for (int i = 0; i < n_rel; ++i) {
+      const double e = std::sqrt(sq[i]);
+      if (per_rel) per_rel[i] = e;
+      sum += e;
+    }
+    if (total) *total = sum;
+    return true;
   }
 
   // completed relation G_i S_ij G_j^T (base.py:119-146)
@@ -1336,6 +1448,7 @@ class Engine : public EngineBase {
     for (auto& rp : rels_) { rp->E.release(); rp->Es.release(); rp->Cx.release(); }
     for (auto& tp : types_) tp->has_factor = true;
     presplit_valid_ = false;
+    products_valid_ = false;
   }
 
  private:
@@ -1392,6 +1505,7 @@ class Engine : public EngineBase {
     cudaFuncSetAttribute(umma_fused1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF1SmemBytes);
     cudaFuncSetAttribute(umma_fused_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes);
     cudaFuncSetAttribute(pinv_spd, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
+    cudaFuncSetAttribute(trace_objective, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
     cudaFuncSetAttribute(backbone_chain<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
   }
   // tensor-core product of a bf16 relation with a split factor:  C (M x k) = op(R) * Gs[g_row0 + ., :]
@@ -1421,8 +1535,10 @@ class Engine : public EngineBase {
   void gram_of(TypeRec& t, cudaStream_t st) {
     const T* Gl = cur(t) + t.row0 * t.k;
     dim3 g(t.gram_chunks, nblk(t.k, 64), nblk(t.k, 64));
-    gram_partial<T><<<g, 256, 0, st>>>(Gl, t.k, Gl, t.k, t.gram_part.template as<double>(), t.rows_loc, t.k, t.k,
-                                       t.gram_rows_per_chunk, 0);
+    if (dmma_) gram_partial_dmma<T><<<g, 256, 0, st>>>(Gl, t.k, Gl, t.k, t.gram_part.template as<double>(), t.rows_loc, t.k, t.k,
+                                                       t.gram_rows_per_chunk);
+    else gram_partial<T><<<g, 256, 0, st>>>(Gl, t.k, Gl, t.k, t.gram_part.template as<double>(), t.rows_loc, t.k, t.k,
+                                            t.gram_rows_per_chunk, 0);
     reduce_partials<<<nblk((long long)t.k * t.k, 32), kRedThreads, 0, st>>>(t.gram_part.template as<double>(), t.gram_raw, t.gram_chunks,
                                                                      (long long)t.k * t.k);
     launches += 2;
@@ -1457,8 +1573,10 @@ class Engine : public EngineBase {
     TypeRec& Ti = *types_[r.ti];
     TypeRec& Tj = *types_[r.tj];
     dim3 g(r.m_chunks, nblk(Ti.k, 64), nblk(Tj.k, 64));
-    gram_partial<T><<<g, 256, 0, st>>>(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.A.template as<T>(), Tj.k, r.M_part.template as<double>(),
-                                       r.rows_loc, Ti.k, Tj.k, r.m_rows_per_chunk, 0);
+    if (dmma_) gram_partial_dmma<T><<<g, 256, 0, st>>>(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.A.template as<T>(), Tj.k,
+                                                       r.M_part.template as<double>(), r.rows_loc, Ti.k, Tj.k, r.m_rows_per_chunk);
+    else gram_partial<T><<<g, 256, 0, st>>>(cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.A.template as<T>(), Tj.k, r.M_part.template as<double>(),
+                                            r.rows_loc, Ti.k, Tj.k, r.m_rows_per_chunk, 0);
     ++launches;
     if (finish) finish_M(r, st, /*local_rows=*/false);
   }
@@ -1475,6 +1593,10 @@ class Engine : public EngineBase {
     ++launches;
   }
   bool corr_deferred() const { return comm_ != nullptr && single_now_ && !no_corr_; }
+  // Sharded handles: the rank-1 part of R^T G_i in the centred form, colsum(R) c_i^T with the column sums over ALL ranks' rows
+  // (all-reduced once per handle), is added to this rank's reduce-scattered rows of B -- 1 / world of initialising every
+  // rank's full-height partial with its local share.
+  void rank1_add_local(RelRec& r, cudaStream_t st);
   // Single-term operand form: G_i^T R G_j = G_i^T (R Gs_j + rowsum c_j^T) + (R^T G_i)^T lo_j, and R^T G_i is B up to second
   // order in the residuals.  The partials land behind the M partials and are summed with them in fp64.
   void corr_M(RelRec& r, cudaStream_t st, bool local_rows);
@@ -1529,6 +1651,17 @@ class Engine : public EngineBase {
       launches += 3;
       CUDA_OK(cudaGetLastError());
       CUDA_OK(cudaStreamSynchronize(st));   // the partial buffer dies here (once per relation and handle)
+    } else {
+      CUDA_OK(cudaMemsetAsync(r.colsum.p, 0, r.colsum.bytes, st));
+    }
+    if (comm_) {     // column sums over every rank's rows (rank1_add_local); every rank gets here at the same relation
+      r.colsum_loc.alloc(r.colsum.bytes, false);
+      CUDA_OK(cudaMemcpyAsync(r.colsum_loc.p, r.colsum.p, r.colsum.bytes, cudaMemcpyDeviceToDevice, st));
+      CUDA_OK(cudaEventRecord(ev_c0_, st));
+      CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
+      NCCL_OK(nccl_api().AllReduce(r.colsum.p, r.colsum.p, (size_t)r.cols, ncclFloat32, ncclSum, comm_, comm_stream_));
+      CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
+      CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));
     }
     r.sums_ready = true;
   }
@@ -1794,11 +1927,11 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   p.tiles_per_split = (tiles + splits - 1) / splits;
   splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.a_atomic = (splits > 1 || single_now_) ? 1 : 0;     // the single-term kernel always reduces into A
-  if (centred_) {    // B starts from the rank-1 part colsum(R) c_i^T of the centred form
+  if (centred_ && comm_ == nullptr) {    // B starts from the rank-1 part colsum(R) c_i^T of the centred form
     rank1_init<<<nblk(Tj.n_pad * Ti.k, 256), 256, 0, st>>>(r.B.template as<float>(), Ti.k, Tj.n_pad, r.cols, Ti.k, r.colsum.template as<float>(),
                                                            Ti.centre.template as<float>());
     ++launches;
-  } else {
+  } else {   // (sharded with its own communicator: the rank-1 part goes onto the reduce-scattered rows instead, rank1_add_local)
     CUDA_OK(cudaMemsetAsync(r.B.p, 0, r.B.bytes, st));
   }
   if (p.a_atomic) CUDA_OK(cudaMemsetAsync(r.A.p, 0, (size_t)r.rows_loc * Tj.k * sizeof(float), st));
@@ -1816,7 +1949,7 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
     const unsigned ctas = (unsigned)std::max<long long>(1, std::min<long long>(sm_count_, units));
     q.dyn_chunk = 0;
     q.work_counter = nullptr;
-    if ((dyn_sched_ == 1 || (dyn_sched_ < 0 && comm_ != nullptr)) && units >= 16ll * ctas) {
+    if (dyn_sched_ == 1 && units >= 16ll * ctas) {
       q.dyn_chunk = (int)std::max<long long>(1, std::min<long long>(16, (units / 4) / (4ll * ctas)));
       q.work_counter = sched_ctr_.template as<int>();
       CUDA_OK(cudaMemsetAsync(q.work_counter, 0, sizeof(int), st));
@@ -1984,6 +2117,17 @@ void Engine<float>::corr_M(RelRec& r, cudaStream_t st, bool local_rows) {
 template <>
 void Engine<double>::corr_M(RelRec&, cudaStream_t, bool) {}
 template <>
+void Engine<float>::rank1_add_local(RelRec& r, cudaStream_t st) {
+  TypeRec& Ti = *types_[r.ti];
+  TypeRec& Tj = *types_[r.tj];
+  if (Tj.rows_loc <= 0) return;
+  rank1_add<<<nblk(Tj.rows_loc * Ti.k, 256), 256, 0, st>>>(r.Bloc.template as<float>(), Ti.k, Tj.rows_loc, Ti.k,
+                                                           r.colsum.template as<float>() + Tj.row0, Ti.centre.template as<float>());
+  ++launches;
+}
+template <>
+void Engine<double>::rank1_add_local(RelRec&, cudaStream_t) {}
+template <>
 void Engine<float>::gate_measure(RelRec& r, int rel, cudaStream_t st) {
   if (r.theta || r.storage != FZ_BF16 || r.rows_loc <= 0) return;
   TypeRec& Ti = *types_[r.ti];
@@ -2014,8 +2158,11 @@ void Engine<float>::gate_measure(RelRec& r, int rel, cudaStream_t st) {
     dim3 grid(1, ksplit);
     if (trans) umma_skinny_kernel<64, true><<<grid, kSkThreads, SkinnyCfg<64>::kSmemBytes, st>>>(r.tmXT, Ti.tmG, p);
     else umma_skinny_kernel<64, false><<<grid, kSkThreads, SkinnyCfg<64>::kSmemBytes, st>>>(r.tmX, Tj.tmG, p);
+    // (sharded with a communicator: the local B partial is kept without its rank-1 part, which the slab norm must include)
+    const bool add_rank1 = trans && comm_ != nullptr && r.colsum_loc.p != nullptr;
     slab_sumsq<<<1, 256, 0, st>>>(p.C, 64, trans ? r.B.template as<float>() : r.A.template as<float>(), trans ? Ti.k : Tj.k, p.M, p.k,
-                                  gate_slots_ + slot + 2 * side);
+                                  gate_slots_ + slot + 2 * side, add_rank1 ? r.colsum_loc.template as<float>() : nullptr,
+                                  add_rank1 ? Ti.centre.template as<float>() : nullptr);
     launches += 2;
   }
 }

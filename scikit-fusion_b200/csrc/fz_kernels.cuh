@@ -191,6 +191,76 @@ gram_partial(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, lo
   }
 }
 
+// The same reduction on the fp64 tensor cores (mma.sync.m8n8k4.f64: DMMA).  Same grid, same partial layout, same 16-row slabs
+// and register prefetch; each of the 8 warps owns 8 rows of the 64 x 64 output tile and sweeps its 8 column tiles, so one
+// shared-memory load of the A fragment feeds 8 MMAs (the CUDA-core version reads 8 doubles per 16 FMAs and runs at ~7 TFLOP/s).
+// Products are exact, accumulation is IEEE fp64: the result equals the CUDA-core kernel's up to the order of the fp64 adds.
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+template <class T>
+__global__ void __launch_bounds__(256)
+gram_partial_dmma(const T* __restrict__ X, long long ldx, const T* __restrict__ Y, long long ldy, double* __restrict__ part,
+                  long long n_rows, int ka, int kb, int rows_per_chunk) {
+  __shared__ double Xs[2][16][64 + 4];      // row pitch 68 doubles: the 4 k-rows of a fragment land 8 banks apart
+  __shared__ double Ys[2][16][64 + 4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a0 = blockIdx.y * 64, b0 = blockIdx.z * 64;
+  const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
+  const long long r_end = min(n_rows, r_begin + rows_per_chunk);
+  double acc[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+  double px[4], py[4];
+  auto fetch = [&](long long r0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      const int rr = idx / 64, cc = idx % 64;
+      double xv = 0.0, yv = 0.0;
+      if (r0 + rr < r_end) {
+        if (a0 + cc < ka) xv = (double)X[(r0 + rr) * ldx + a0 + cc];
+        if (b0 + cc < kb) yv = (double)Y[(r0 + rr) * ldy + b0 + cc];
+      }
+      px[e] = xv;
+      py[e] = yv;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      Xs[buf][idx / 64][idx % 64] = px[e];
+      Ys[buf][idx / 64][idx % 64] = py[e];
+    }
+  };
+  int buf = 0;
+  if (r_begin < r_end) fetch(r_begin);
+  const int kr = lane & 3, mc = lane >> 2;      // fragment coordinates: k-row inside the step, row (A) / column (B) of the 8 x 8 tile
+  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+    stash(buf);
+    __syncthreads();
+    if (r0 + 16 < r_end) fetch(r0 + 16);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const double a = Xs[buf][4 * ks + kr][8 * warp + mc];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[j], a, Ys[buf][4 * ks + kr][8 * j + mc]);
+    }
+    buf ^= 1;
+  }
+  double* out = part + (long long)blockIdx.x * ka * kb;
+  const int a = a0 + 8 * warp + mc;
+  if (a < ka) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + 8 * j + 2 * kr;
+      if (b < kb) out[(long long)a * kb + b] = acc[j][0];
+      if (b + 1 < kb) out[(long long)a * kb + b + 1] = acc[j][1];
+    }
+  }
+}
+
 // out[i] = sum_c part[c][i], deterministic: block = 32 consecutive elements x 32 chunk lanes (warp w sums the chunks
 // w, w+32, ... in order, four independent loads in flight), then the 32 lane sums are added in fixed order.
 // grid = ceil(elems / 32), 1024 threads.
@@ -518,6 +588,20 @@ __global__ void col_sumsq_partial(const XT* __restrict__ X, long long ld, long l
   }
   part[(long long)blockIdx.y * cols + c] = s;
 }
+// out[0] = sum of v[0..n) in a fixed order (one block)
+__global__ void __launch_bounds__(1024)
+total_sum(const double* __restrict__ v, long long n, double* __restrict__ out) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) s += v[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
 __global__ void sqrt_of_chunk_sums(const double* __restrict__ part, double* __restrict__ out, int chunks, long long cols) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
@@ -648,12 +732,16 @@ __global__ void finish_col_sums(const double* __restrict__ part, float* __restri
 // out[0] = sum of squares of X (rows x k, leading dimension ldx), out[1] = the same of Y: one block, fixed order.
 // (single-term gate: X = slab product with the residual term, Y = the matching rows of A or B)
 __global__ void __launch_bounds__(256)
-slab_sumsq(const float* __restrict__ X, long long ldx, const float* __restrict__ Y, long long ldy, int rows, int k, double* __restrict__ out) {
+slab_sumsq(const float* __restrict__ X, long long ldx, const float* __restrict__ Y, long long ldy, int rows, int k, double* __restrict__ out,
+           const float* __restrict__ y_rowscale = nullptr, const float* __restrict__ y_centre = nullptr) {
+  // y_rowscale / y_centre: Y is taken as Y + y_rowscale[r] * y_centre[q] (a rank-1 part that is kept apart from the stored Y)
   __shared__ double rx[256], ry[256];
   double sx = 0.0, sy = 0.0;
   for (int o = threadIdx.x; o < rows * k; o += 256) {
     const int r = o / k, q = o % k;
-    const double x = X[(long long)r * ldx + q], y = Y[(long long)r * ldy + q];
+    const double x = X[(long long)r * ldx + q];
+    double y = Y[(long long)r * ldy + q];
+    if (y_rowscale != nullptr) y += (double)y_rowscale[r] * (double)y_centre[q];
     sx += x * x;
     sy += y * y;
   }
@@ -675,6 +763,15 @@ __global__ void rank1_init(float* __restrict__ B, long long ldb, long long n_row
   const int q = (int)(idx % k);
   B[r * ldb + q] = (r < n_valid) ? colsum[r] * centre[q] : 0.f;
 }
+// B[r][q] += colsum[r] * centre[q] on a block of rows (the rank-1 part, added after a reduce-scatter)
+__global__ void rank1_add(float* __restrict__ B, long long ldb, long long n_rows, int k, const float* __restrict__ colsum,
+                          const float* __restrict__ centre) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * k) return;
+  const long long r = idx / k;
+  const int q = (int)(idx % k);
+  B[r * ldb + q] += colsum[r] * centre[q];
+}
 // First-order restoration of the residual term in the backbone solve: part[chunk][a][b] = sum_r B[r][a] * lo[r][b],
 // lo[r][b] = (G[r][b] - centre[b]) - Gs[r][b]  (exact in fp32).  The correction is 2^-9 of M, so fp32 accumulation per
 // chunk (and fp64 across chunks) is ample.  grid = (chunks, ceil(ka/64), ceil(kb/64)), 256 threads, 4x4 per thread.
@@ -682,8 +779,9 @@ __global__ void __launch_bounds__(256)
 corr_partial(const float* __restrict__ B, long long ldb, const float* __restrict__ G, long long ldg,
              const __nv_bfloat16* __restrict__ Gs, long long ldgs, const float* __restrict__ centre, double* __restrict__ part,
              long long n_rows, int ka, int kb, int rows_per_chunk) {
-  __shared__ float Xs[16][64 + 4];
-  __shared__ float Ys[16][64 + 4];
+  // 16-row slabs, double-buffered; the next slab's global loads are in flight while the current one is multiplied
+  __shared__ float Xs[2][16][64 + 4];
+  __shared__ float Ys[2][16][64 + 4];
   const int tid = threadIdx.x;
   const int a0 = blockIdx.y * 64, b0 = blockIdx.z * 64;
   const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
@@ -694,7 +792,8 @@ corr_partial(const float* __restrict__ B, long long ldb, const float* __restrict
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+  float px[4], py[4];
+  auto fetch = [&](long long r0) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int idx = tid + e * 256;
@@ -704,23 +803,34 @@ corr_partial(const float* __restrict__ B, long long ldb, const float* __restrict
         if (a0 + cc < ka) xv = B[(r0 + rr) * ldb + a0 + cc];
         if (b0 + cc < kb) yv = (G[(r0 + rr) * ldg + b0 + cc] - centre[b0 + cc]) - __bfloat162float(Gs[(r0 + rr) * ldgs + b0 + cc]);
       }
-      Xs[rr][cc] = xv;
-      Ys[rr][cc] = yv;
+      px[e] = xv;
+      py[e] = yv;
+    }
+  };
+  int buf = 0;
+  if (r_begin < r_end) fetch(r_begin);
+  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      Xs[buf][idx / 64][idx % 64] = px[e];
+      Ys[buf][idx / 64][idx % 64] = py[e];
     }
     __syncthreads();
+    if (r0 + 16 < r_end) fetch(r0 + 16);
 #pragma unroll
     for (int rr = 0; rr < 16; ++rr) {
       float a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = Xs[rr][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) a[i] = Xs[buf][rr][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Ys[rr][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = Ys[buf][rr][tx * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-    __syncthreads();
+    buf ^= 1;
   }
   double* out = part + (long long)blockIdx.x * ka * kb;
 #pragma unroll

@@ -329,6 +329,10 @@ class Engine(object):
         rid = self._ck(self._L.fz_add_relation(self._h, ti, tj, ptr, ld, code, mem, st, 1 if borrow else 0, mptr, mld, mmem))
         if borrow:
             self._keep.append(keep)
+        if st == FZ_BF16 and self.relation_device_ptr(rid)[2] != FZ_BF16:
+            import warnings
+            warnings.warn("relation %d was asked to be stored in bfloat16 but is kept in the compute dtype (constraint matrices and "
+                          "masked relations stay exact: they run on the CUDA-core path, not on the tensor cores)" % rid, RuntimeWarning)
         self.rel_types.append((ti, tj))
         return rid
 
