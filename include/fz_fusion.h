@@ -72,6 +72,12 @@ int fz_comm_init(fz_engine* e, const void* unique_id128);
 int fz_group_comm_init(fz_engine** engines, int n);
 int fz_group_iterate(fz_engine** engines, int n, int algo, int n_iters);      /* fz_iterate on the NULL stream + synchronise */
 int fz_group_objective(fz_engine** engines, int n, double* per_relation, double* total);
+/* device-side initialisation (below) on a shard group driven from one process: the calls hold collectives, so each runs on
+ * one host thread per handle.  `count` = entries of dst_host (the full vector: columns for axis 0, rows of the row type for 1). */
+int fz_group_init_fill(fz_engine** engines, int n, int t, double value);
+int fz_group_relation_norms(fz_engine** engines, int n, int rel, int axis, double* dst_host, int64_t count);
+int fz_group_init_add_sampled_means(fz_engine** engines, int n, int t, int rel, const int32_t* idx_host, int p_c);
+int fz_group_init_end(fz_engine** engines, int n);
 /* returns the type id (>= 0).  n = number of objects (global), k = factorization rank. */
 int fz_add_type(fz_engine* e, int64_t n, int k);
 /* Relation between row type ti and column type tj; ti == tj declares a constraint matrix Theta_t.
@@ -162,7 +168,9 @@ int fz_profile_product(fz_engine* e, int ti, int tj, const void* M, int64_t ldm,
  * computes the column means (a product with a 0/1 selection matrix through the streamed kernels) and accumulates
  *     G_t = value + sum_relations | mean of the sampled columns |                      (_init.py:36-39, 57-60).
  * Call order: fz_finalize, then per type fz_init_fill + fz_init_add_sampled_means per relation, then fz_init_end (which
- * marks every factor as set).  p_c == 0 (fewer than 5 columns) yields NaN factors, as upstream.  Unsharded handles only.
+ * marks every factor as set).  p_c == 0 (fewer than 5 columns) yields NaN factors, as upstream.  Sharded handles need their
+ * communicator (fz_comm_init): every rank makes the same calls with the same plans; column norms are summed and the sampled
+ * means all-gathered / all-reduced, so every rank ends with the same full factors.
  * fz_relation_norms returns the 2-norms of the columns (axis 0) or rows (axis 1) of a relation in a HOST buffer: random_c
  * samples from the int(0.5 * cols) columns of largest norm (_init.py:30-34). */
 int fz_init_fill(fz_engine* e, int t, double value, void* stream);

@@ -1363,42 +1363,73 @@ class Engine : public EngineBase {
   }
   // 2-norms of the columns (axis 0) or rows (axis 1) of a relation, fp64, into a HOST buffer (random_c ranks the
   // columns of the oriented relation by norm, _init.py:32-34)
+  // Sharded handles (with their own communicator): column norms are summed over the ranks' row blocks, row norms are
+  // all-gathered, so every rank returns the same full vector.
   void relation_norms(int rel, int axis, double* dst_host, cudaStream_t st) override {
     need_final();
-    if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "device initialisation on sharded handles is not implemented");
+    if (world_ != 1 && !comm_) FZ_THROW(FZ_ERR_UNSUPPORTED, "device initialisation on a sharded handle needs fz_comm_init");
     RelRec& r = relation(rel);
     if (r.theta) FZ_THROW(FZ_ERR_INVALID, "constraint matrices do not seed factors");
     if (axis != 0 && axis != 1) FZ_THROW(FZ_ERR_INVALID, "axis must be 0 (column norms) or 1 (row norms)");
     if (dst_host == nullptr) FZ_THROW(FZ_ERR_INVALID, "null destination");
-    const int64_t count = axis == 0 ? r.cols : r.rows_loc;
+    TypeRec& Ti = *types_[r.ti];
+    const int64_t count = axis == 0 ? r.cols : Ti.n;
     DevBuf out;
-    out.alloc((size_t)std::max<int64_t>(1, count) * 8);
+    out.alloc((size_t)std::max<int64_t>(1, axis == 0 ? r.cols : Ti.n_pad) * 8);
     if (axis == 0) {
       const int chunks = (int)std::min<int64_t>(64, std::max<int64_t>(1, (r.rows_loc + 255) / 256));
       const int64_t rows_per_chunk = (r.rows_loc + chunks - 1) / chunks;
       DevBuf part;
       part.alloc((size_t)chunks * r.cols * 8);
       dim3 g(nblk(r.cols, 256), chunks);
-      if (r.storage == FZ_BF16) col_sumsq_partial<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, rows_per_chunk, part.template as<double>());
-      else col_sumsq_partial<T><<<g, 256, 0, st>>>((const T*)r.data, r.ld, r.rows_loc, r.cols, rows_per_chunk, part.template as<double>());
-      sqrt_of_chunk_sums<<<nblk(r.cols, 256), 256, 0, st>>>(part.template as<double>(), out.template as<double>(), chunks, r.cols);
-      launches += 2;
+      if (r.rows_loc > 0) {
+        if (r.storage == FZ_BF16) col_sumsq_partial<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, rows_per_chunk, part.template as<double>());
+        else col_sumsq_partial<T><<<g, 256, 0, st>>>((const T*)r.data, r.ld, r.rows_loc, r.cols, rows_per_chunk, part.template as<double>());
+      }
+      sum_chunks<<<nblk(r.cols, 256), 256, 0, st>>>(part.template as<double>(), out.template as<double>(), chunks, r.cols);
+      if (comm_) all_reduce_on(out.p, (size_t)r.cols, ncclFloat64, st);
+      sqrt_inplace<<<nblk(r.cols, 256), 256, 0, st>>>(out.template as<double>(), r.cols);
+      launches += 3;
       CUDA_OK(cudaGetLastError());
       CUDA_OK(cudaMemcpyAsync(dst_host, out.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
     } else {
-      if (r.storage == FZ_BF16) row_norms<__nv_bfloat16><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, out.template as<double>());
-      else row_norms<T><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const T*)r.data, r.ld, r.rows_loc, r.cols, out.template as<double>());
-      ++launches;
+      double* mine = out.template as<double>() + Ti.row0;
+      if (r.rows_loc > 0) {
+        if (r.storage == FZ_BF16) row_norms<__nv_bfloat16><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, mine);
+        else row_norms<T><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const T*)r.data, r.ld, r.rows_loc, r.cols, mine);
+        ++launches;
+      }
       CUDA_OK(cudaGetLastError());
+      if (comm_) all_gather_on(out.p, (size_t)Ti.m_loc, ncclFloat64, st);
       CUDA_OK(cudaMemcpyAsync(dst_host, out.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
     }
   }
-  // idx_host: [k_t][p_c] column indices of the oriented relation (t on the rows), one row per latent column
+  // collectives of the set-up steps: on the communicator's stream, fenced on both sides against `st`
+  void all_reduce_on(void* buf, size_t count, ncclDataType_t dt, cudaStream_t st) {
+    CUDA_OK(cudaEventRecord(ev_c0_, st));
+    CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
+    NCCL_OK(nccl_api().AllReduce(buf, buf, count, dt, ncclSum, comm_, comm_stream_));
+    CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
+    CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));
+  }
+  // in place: this rank's `count_per_rank` elements sit at offset rank * count_per_rank of `buf`
+  void all_gather_on(void* buf, size_t count_per_rank, ncclDataType_t dt, cudaStream_t st) {
+    const size_t es = (dt == ncclFloat64) ? 8 : 4;
+    CUDA_OK(cudaEventRecord(ev_c0_, st));
+    CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
+    NCCL_OK(nccl_api().AllGather((const char*)buf + (size_t)rank_ * count_per_rank * es, buf, count_per_rank, dt, comm_, comm_stream_));
+    CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
+    CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));
+  }
+  // idx_host: [k_t][p_c] column indices of the oriented relation (t on the rows), one row per latent column.
+  // Sharded: the means of a row-role relation are computed for the local rows and all-gathered, those of a column-role
+  // relation are partial sums over the local rows and all-reduced (before the absolute value: it is not linear); every rank
+  // then adds them to its full copy of the factor.
   void init_add_sampled_means(int t, int rel, const int32_t* idx_host, int p_c, cudaStream_t st) override {
     need_final();
-    if (world_ != 1) FZ_THROW(FZ_ERR_UNSUPPORTED, "device initialisation on sharded handles is not implemented");
+    if (world_ != 1 && !comm_) FZ_THROW(FZ_ERR_UNSUPPORTED, "device initialisation on a sharded handle needs fz_comm_init");
     if (t < 0 || t >= (int)types_.size()) FZ_THROW(FZ_ERR_INVALID, "unknown type id %d", t);
     RelRec& r = relation(rel);
     if (r.theta || (r.ti != t && r.tj != t)) FZ_THROW(FZ_ERR_INVALID, "relation %d does not touch type %d", rel, t);
@@ -1407,7 +1438,7 @@ class Engine : public EngineBase {
     const bool row_role = (r.ti == t);
     TypeRec& To = row_role ? *types_[r.tj] : *types_[r.ti];     // the type the sampled columns index
     // W (n_other x k_t), ones at the sampled positions
-    r.E.alloc((size_t)To.n * Tt.k * sizeof(T));
+    r.E.alloc((size_t)To.n_pad * Tt.k * sizeof(T));
     if (p_c > 0) {
       DevBuf idx;
       idx.alloc((size_t)Tt.k * p_c * sizeof(int32_t), false);
@@ -1417,19 +1448,31 @@ class Engine : public EngineBase {
       CUDA_OK(cudaGetLastError());
       CUDA_OK(cudaStreamSynchronize(st));                       // idx is freed at scope exit
     }
-    r.Cx.alloc((size_t)Tt.n * Tt.k * sizeof(T));
-    if (r.storage == FZ_BF16) {
-      r.Es.alloc((size_t)To.n * gs_terms_ * kKp * 2);
-      split_factor<T><<<nblk(To.n * kKp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(), To.n, To.n,
-                                                              Tt.k, kKp, gs_terms_);
-      ++launches;
-      std::string e;
-      if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 64, &e))
-        FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
-      umma(r, /*trans=*/!row_role, r.tmEs, 0, r.Cx.template as<T>(), Tt.k, (int)Tt.n, (int)To.n, Tt.k, st);
-    } else {
-      if (row_role) gemm((const T*)r.data, r.ld, r.E.template as<T>(), Tt.k, r.Cx.template as<T>(), Tt.k, (int)Tt.n, Tt.k, (int)To.n, false, st);
-      else gemm_t((const T*)r.data, r.ld, r.E.template as<T>(), Tt.k, r.Cx.template as<T>(), Tt.k, (int)Tt.n, Tt.k, (int)To.n, st);
+    r.Cx.alloc((size_t)Tt.n_pad * Tt.k * sizeof(T));            // zeroed: rows this rank does not compute stay 0
+    // local rows of the relation: row role -> rows [row0, row0 + rows_loc) of the result; column role -> a partial of all rows
+    T* C = r.Cx.template as<T>() + (row_role ? Tt.row0 * Tt.k : 0);
+    const int M = (int)(row_role ? r.rows_loc : Tt.n);
+    const int K = (int)(row_role ? To.n : r.rows_loc);
+    if (r.rows_loc > 0) {
+      if (r.storage == FZ_BF16) {
+        r.Es.alloc((size_t)To.n_pad * gs_terms_ * kKp * 2);
+        split_factor<T><<<nblk(To.n_pad * kKp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(), To.n, To.n_pad,
+                                                                    Tt.k, kKp, gs_terms_);
+        ++launches;
+        std::string e;
+        if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n_pad, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 64, &e))
+          FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+        umma(r, /*trans=*/!row_role, r.tmEs, row_role ? 0 : To.row0, C, Tt.k, M, K, Tt.k, st);
+      } else {
+        const T* W = r.E.template as<T>() + (row_role ? 0 : To.row0 * Tt.k);
+        if (row_role) gemm((const T*)r.data, r.ld, W, Tt.k, C, Tt.k, M, Tt.k, K, false, st);
+        else gemm_t((const T*)r.data, r.ld, W, Tt.k, C, Tt.k, M, Tt.k, K, st);
+      }
+    }
+    if (comm_) {
+      const ncclDataType_t dt = (kDT == FZ_F32) ? ncclFloat32 : ncclFloat64;
+      if (row_role) all_gather_on(r.Cx.p, (size_t)Tt.m_loc * Tt.k, dt, st);
+      else all_reduce_on(r.Cx.p, (size_t)Tt.n * Tt.k, dt, st);
     }
     add_abs_mean<T><<<nblk(Tt.n * Tt.k, 256), 256, 0, st>>>(r.Cx.template as<T>(), cur(Tt), Tt.n * Tt.k, (T)p_c);
     ++launches;
@@ -2371,6 +2414,26 @@ int fz_group_iterate(fz_engine** engines, int n, int algo, int n_iters) {
     DeviceGuard guard(e->impl->device);
     return cudaStreamSynchronize(nullptr) == cudaSuccess ? (int)FZ_OK : (int)FZ_ERR_CUDA;
   });
+}
+int fz_group_init_fill(fz_engine** engines, int n, int t, double value) {
+  return for_each_engine(engines, n, [&](fz_engine* e) { return fz_init_fill(e, t, value, nullptr); });
+}
+int fz_group_relation_norms(fz_engine** engines, int n, int rel, int axis, double* dst_host, int64_t count) {
+  // every rank computes (and takes part in the collective); rank 0 writes the caller's buffer, the others scratch copies
+  if (count < 0) return FZ_ERR_INVALID;
+  std::vector<std::vector<double>> scratch((size_t)std::max(0, n));
+  for (int i = 1; i < n; ++i) scratch[(size_t)i].resize((size_t)count + 1);
+  return for_each_engine(engines, n, [&](fz_engine* e) {
+    int i = 0;
+    while (i < n && engines[i] != e) ++i;
+    return fz_relation_norms(e, rel, axis, i == 0 ? dst_host : scratch[(size_t)i].data(), nullptr);
+  });
+}
+int fz_group_init_add_sampled_means(fz_engine** engines, int n, int t, int rel, const int32_t* idx_host, int p_c) {
+  return for_each_engine(engines, n, [&](fz_engine* e) { return fz_init_add_sampled_means(e, t, rel, idx_host, p_c, nullptr); });
+}
+int fz_group_init_end(fz_engine** engines, int n) {
+  return for_each_engine(engines, n, [&](fz_engine* e) { return fz_init_end(e); });
 }
 int fz_group_objective(fz_engine** engines, int n, double* per_relation, double* total) {
   // every rank computes its share and takes part in the all-reduce; rank 0's (identical) result is returned

@@ -609,6 +609,10 @@ __global__ void sqrt_of_chunk_sums(const double* __restrict__ part, double* __re
   for (int k = 0; k < chunks; ++k) s += part[(long long)k * cols + c];
   out[c] = sqrt(s);
 }
+__global__ void sqrt_inplace(double* __restrict__ v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = sqrt(v[i]);
+}
 // one warp per row, lanes stride over the columns, fixed-order shuffle reduction
 template <class XT>
 __global__ void row_norms(const XT* __restrict__ X, long long ld, long long rows, long long cols, double* __restrict__ out) {

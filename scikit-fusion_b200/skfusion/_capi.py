@@ -22,7 +22,8 @@ FZ_TERMS_AUTO, FZ_TERMS_CENTRED1 = 0, -1
 # every symbol include/fz_fusion.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "fz_create", "fz_destroy", "fz_last_error", "fz_version", "fz_launch_count", "fz_set_shard", "fz_comm_unique_id", "fz_comm_init", "fz_group_comm_init", "fz_group_iterate",
-    "fz_group_objective", "fz_add_type",
+    "fz_group_objective", "fz_group_init_fill", "fz_group_relation_norms", "fz_group_init_add_sampled_means",
+    "fz_group_init_end", "fz_add_type",
     "fz_add_relation", "fz_set_factor", "fz_set_backbone", "fz_set_split_terms", "fz_operand_stats", "fz_finalize", "fz_iterate", "fz_pair_iterate", "fz_relation_device_ptr",
     "fz_phase_products", "fz_phase_update", "fz_phase_products_begin", "fz_phase_product_relation", "fz_phase_products_end", "fz_comm_small", "fz_comm_bpartial", "fz_comm_factor",
     "fz_transform_prepare", "fz_transform_iterate", "fz_get_factor", "fz_get_backbone", "fz_objective", "fz_complete", "fz_profile_product",
@@ -86,6 +87,10 @@ def lib():
         "fz_group_comm_init": (i32, [c_void_pp, i32]),
         "fz_group_iterate": (i32, [c_void_pp, i32, i32, i32]),
         "fz_group_objective": (i32, [c_void_pp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+        "fz_group_init_fill": (i32, [c_void_pp, i32, i32, ctypes.c_double]),
+        "fz_group_relation_norms": (i32, [c_void_pp, i32, i32, i32, ctypes.POINTER(ctypes.c_double), i64]),
+        "fz_group_init_add_sampled_means": (i32, [c_void_pp, i32, i32, i32, ctypes.POINTER(ctypes.c_int32), i32]),
+        "fz_group_init_end": (i32, [c_void_pp, i32]),
         "fz_add_type": (i32, [vp, i64, i32]),
         "fz_add_relation": (i32, [vp, i32, i32, vp, i64, i32, i32, i32, i32, vp, i64, i32]),
         "fz_set_factor": (i32, [vp, i32, vp, i64, i32, i32]),
@@ -181,6 +186,28 @@ class EngineGroup(object):
         tot = ctypes.c_double()
         self._ck(self._L.fz_group_objective(self._arr, len(self.engines), per, ctypes.byref(tot)))
         return tot.value, list(per)[:n_relations]
+
+    # ---- device-side initialisation on the whole group (same signatures as Engine's, so initializers.initialize_on_device
+    # drives either): every call holds a collective and runs on one host thread per handle
+    def init_fill(self, t, value):
+        self._ck(self._L.fz_group_init_fill(self._arr, len(self.engines), int(t), float(value)))
+
+    def relation_norms(self, rel, axis):
+        head = self.engines[0]
+        ti, tj = head.rel_types[rel]
+        count = head.type_shape[tj][0] if axis == 0 else head.type_shape[ti][0]
+        out = np.empty(count, dtype=np.float64)
+        self._ck(self._L.fz_group_relation_norms(self._arr, len(self.engines), int(rel), int(axis),
+                                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), count))
+        return out
+
+    def init_add_sampled_means(self, t, rel, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        self._ck(self._L.fz_group_init_add_sampled_means(self._arr, len(self.engines), int(t), int(rel),
+                                                         idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(idx.shape[1])))
+
+    def init_end(self):
+        self._ck(self._L.fz_group_init_end(self._arr, len(self.engines)))
 
     def close(self):
         for e in self.engines:

@@ -226,8 +226,11 @@ def _fit_sharded(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_typ
     world = int(opts["n_gpus"])
     base = int(opts["device"])
     sizes = count_objects(obj_types, R)
-    first = {key: _host_view(mats[0]) for key, mats in R.items()} if init_type != "random" else {}
-    G0 = initialize(obj_types, sizes, obj_type2rank, first, init_type, random_state)     # on the host: RNG-exact
+    on_device = _init_on_device(opts, init_type, R, Theta)
+    G0 = None
+    if not on_device:
+        first = {key: _host_view(mats[0]) for key, mats in R.items()} if init_type != "random" else {}
+        G0 = initialize(obj_types, sizes, obj_type2rank, first, init_type, random_state)     # on the host: RNG-exact
     if stopping_system:
         compute_err = True
     probs = []
@@ -244,12 +247,20 @@ def _fit_sharded(algo, R, M, Theta, obj_types, obj_type2rank, max_iter, init_typ
                 masks = {key: [None if m is None else _row_block(m, *local_rows(sizes[key[0]], world, p), base + p) for m in ms]
                          for key, ms in M.items()}
             prob.add_blocks(block(R), block(Theta), masks)
-            for t in obj_types:
-                prob.engine.set_factor(prob.type_id[t], G0[t, t])
+            if not on_device:
+                for t in obj_types:
+                    prob.engine.set_factor(prob.type_id[t], G0[t, t])
             prob.engine.finalize()
         group = _capi.EngineGroup([prob.engine for prob in probs])
         group.comm_init()
         head = probs[0]
+        if on_device:
+            # random_c / random_vcol with the O(k n^2) column means on the GPUs: the host keeps the RandomState, every rank
+            # computes its rows' share and the group calls carry the collectives (include/fz_fusion.h: fz_group_init_*)
+            initialize_on_device(group, head.type_id, {key: ids[0] for key, ids in head.rel_ids.items()}, list(obj_types),
+                                 obj_type2rank, list(R.keys()), sizes, init_type, random_state)
+            if max_iter <= 0 or stopping or compute_err or callback:
+                G0 = head.factors()
         if not (stopping or compute_err or callback):
             if max_iter > 0:
                 group.iterate(algo, max_iter)

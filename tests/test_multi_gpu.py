@@ -93,3 +93,21 @@ def test_completion_on_two_gpus_equals_the_oracle():
                            dtype="float64", n_gpus=2)
     assert max(rel_fro(Go[t, t], G[t, t]) for t in types) < 1e-8
     assert max(rel_fro(So[k][0], S[k][0]) for k in So) < 1e-7
+
+
+@pytest.mark.parametrize("init", ["random_c", "random_vcol"])
+def test_device_side_initialisation_on_two_gpus_equals_the_host_initialisation(init):
+    """The data-driven seeds with their column means computed by the shard group (norms summed over the ranks, means
+    all-gathered / all-reduced) against the reference-order host initialisation: same RandomState consumption, same factors."""
+    if _gpus() < 2:
+        pytest.skip("needs two GPUs")
+    from skfusion.fusion import solver
+    types, ranks, R = oracle.synthetic_graph(333, n_types=3, rank=12)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Gh, Sh = solver.dfmf(R, {}, types, ranks, max_iter=4, init_type=init, random_state=np.random.RandomState(8),
+                             dtype="float64", n_gpus=2, device_init=False)
+        Gd, Sd = solver.dfmf(R, {}, types, ranks, max_iter=4, init_type=init, random_state=np.random.RandomState(8),
+                             dtype="float64", n_gpus=2, device_init=True)
+    assert max(rel_fro(Gh[t, t], Gd[t, t]) for t in types) < 1e-9
+    assert max(rel_fro(Sh[k][0], Sd[k][0]) for k in Sh) < 1e-7

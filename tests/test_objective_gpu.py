@@ -73,7 +73,8 @@ def test_nearly_exact_fit_takes_the_explicit_form():
     try:
         eng.iterate(_capi.FZ_DFMF, 3)
         total, _ = eng.objective(1)
-        assert hist[-1] < 1e-3 * np.linalg.norm(R["a", "b"][0])
-        assert abs(total - hist[-1]) <= 1e-6 * max(hist[-1], 1e-12) + 1e-10
+        norm_r = np.linalg.norm(R["a", "b"][0])
+        assert hist[-1] < 1e-3 * norm_r
+        assert abs(total - hist[-1]) <= 1e-9 * norm_r          # both are rounding noise around an exact fit
     finally:
         eng.close()
