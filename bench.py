@@ -44,8 +44,8 @@ def parse():
     ap.add_argument("--cpu-sizes", default="4096,8192,16384", help="objects per type of the CPU arm's bounded samples")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "readme3", "dicty", "transform"],
-                    help="synthetic = the contract workload; readme3 / dicty = the small BASELINE configs C1 / C2 "
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "readme3", "dicty", "movielens", "transform"],
+                    help="synthetic = the contract workload; readme3 / dicty / movielens = the small BASELINE configs C1 / C2 / C3 "
                          "(latency-bound; informational line, N=1 only); transform = config C5 (project 10 000 new "
                          "rows of type 0 against a 100 000-object model, 4 relations; informational line, N=1 only)")
     args = ap.parse_args()
@@ -493,7 +493,9 @@ def small_workload(args):
     import cases
     import fusion_oracle as oracle
     from skfusion import _capi
-    case = cases.dicty_case() if args.workload == "dicty" else cases.fit_cases()["readme3"]
+    case = {"dicty": cases.dicty_case, "movielens": cases.movielens_case}.get(args.workload, lambda: cases.fit_cases()["readme3"])()
+    completion = case.get("algo") == "dfmc"         # C3 is a matrix-completion fit (Dfmc): masked entries re-imputed every iteration
+    algo = _capi.FZ_DFMC if completion else _capi.FZ_DFMF
     sizes = oracle.count_objects(case["R"])
     import warnings
     warnings.simplefilter("ignore")
@@ -503,32 +505,37 @@ def small_workload(args):
     tid = {t: eng.add_type(sizes[t], case["ranks"][t]) for t in case["types"]}
     for blocks in (case["R"], case["Theta"]):
         for (a, b), mats in blocks.items():
-            for m in mats:
-                eng.add_relation(tid[a], tid[b], m)
+            for l, m in enumerate(mats):
+                mask = case["M"][a, b][l] if (completion and blocks is case["R"]) else None
+                eng.add_relation(tid[a], tid[b], m, mask=mask)
     for t in case["types"]:
         eng.set_factor(tid[t], G0[t, t])
     eng.finalize()
     st = torch.cuda.current_stream().cuda_stream
-    eng.iterate(_capi.FZ_DFMF, max(3, args.warmup), st)
+    eng.iterate(algo, max(3, args.warmup), st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = eng.launches
     e0.record()
-    eng.iterate(_capi.FZ_DFMF, args.steps, st)
+    eng.iterate(algo, args.steps, st)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     launches = eng.launches - l0
     eng.close()
     stamps = []
-    oracle.dfmf(case["R"], case["Theta"], case["types"], case["ranks"], max_iter=args.steps + 2, G0=G0,
-                callback=lambda G, S, it: stamps.append(time.perf_counter()))
+    if completion:
+        oracle.dfmc(case["R"], case["M"], case["Theta"], case["types"], case["ranks"], max_iter=min(args.steps, 20) + 2, G0=G0,
+                    callback=lambda G, S, it: stamps.append(time.perf_counter()))
+    else:
+        oracle.dfmf(case["R"], case["Theta"], case["types"], case["ranks"], max_iter=args.steps + 2, G0=G0,
+                    callback=lambda G, S, it: stamps.append(time.perf_counter()))
     cpu_it = 1.0 / float(np.median(np.diff(stamps)))
-    print(json.dumps({"metric": "DFMF iterations/sec, BASELINE config %s" % args.workload, "value": round(1000.0 / ms, 1),
+    print(json.dumps({"metric": "%s iterations/sec, BASELINE config %s" % ("DFMC" if completion else "DFMF", args.workload), "value": round(1000.0 / ms, 1),
                       "unit": "it/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": round(ms, 4), "dtype": "f32",
                       "gpu_launches": launches, "launches_per_step": launches / float(args.steps),
                       "cpu_baseline": {"value": round(cpu_it, 1), "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
-                                       "sample": "oracle dfmf on the same inputs, all host BLAS threads"},
+                                       "sample": "oracle %s on the same inputs, all host BLAS threads" % ("dfmc" if completion else "dfmf")},
                       "note": "latency-bound: no roofline claim (SURVEY.md 8d)"}))
 
 
