@@ -20,12 +20,14 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/fz_fusion.h"
 #include "fz_chain.cuh"
 #include "fz_kernels.cuh"
 #include "nccl_shim.h"
+#include "peer_reduce.cuh"
 #include "tmap.h"
 #include "umma_fused.cuh"
 #include "umma_fused1.cuh"
@@ -320,6 +322,15 @@ class Engine : public EngineBase {
   cudaEvent_t ev_c0_ = nullptr, ev_c1_ = nullptr, ev_gram_ = nullptr, ev_gram_done_ = nullptr;
   std::vector<cudaEvent_t> ev_upd_, ev_gather_, ev_rs_;
   std::vector<char> gather_pending_;
+  // ---- reduce-scatter of the B partials over NVLink peer memory (peer_reduce.cuh); NCCL's stays the fall-back
+  int peer_mode_ = -1;          // -1 not set up yet, 0 unavailable / disabled (FZ_PEER_RS=0), 1 active
+  unsigned long long peer_epoch_ = 0;
+  DevBuf peer_flags_;           // [2][world][n_rel] u64: arrive | consumed, written by the peers
+  DevBuf peer_done_;            // [n_rel] u32: finished-block counters of pull_reduce
+  PeerFlags peer_flag_ptrs_;
+  std::vector<PeerPtrs> peer_B_;          // per relation: every rank's partial buffer as mapped in this process
+  std::vector<void*> peer_opened_;        // IPC mappings to close
+  cudaEvent_t ev_sig_ = nullptr;
   int64_t gram_count_ = 0;      // leading doubles of small_ that hold the Gram sums (all-reduced ahead of the rest)
   bool pinv_done_ = false;      // this iteration's pseudo-inverses already ran beside the products
   // operand forms of the NEXT iteration are built per type right behind that type's update (and all-gather), beside the
@@ -387,6 +398,8 @@ class Engine : public EngineBase {
  public:
   explicit Engine(int device) : device_(device) { this->device = device; }
   ~Engine() override {
+    for (void* q : peer_opened_) cudaIpcCloseMemHandle(q);
+    if (ev_sig_) cudaEventDestroy(ev_sig_);
     if (comm_) nccl_api().CommDestroy(comm_);
     if (comm_stream_) cudaStreamDestroy(comm_stream_);
     for (auto e : {ev_c0_, ev_c1_, ev_gram_, ev_gram_done_}) if (e) cudaEventDestroy(e);
@@ -783,14 +796,34 @@ class Engine : public EngineBase {
     const int algo = FZ_DFMF;
     const NcclApi& nc = nccl_api();
     const ncclDataType_t dt = (kDT == FZ_F32) ? ncclFloat32 : ncclFloat64;
+    if (peer_mode_ < 0) peer_setup(st);
+    ++peer_epoch_;
     phase_products_begin(algo, st);
     for (size_t r = 0; r < rels_.size(); ++r) {
       phase_product_relation(algo, (int)r, st);
       RelRec& rel = *rels_[r];
       if (rel.theta) continue;
-      CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_rel_[r], 0));            // this relation's B partial is complete
-      NCCL_OK(nc.ReduceScatter(rel.B.p, rel.Bloc.p, (size_t)types_[rel.tj]->m_loc * types_[rel.ti]->k, dt, ncclSum, comm_, comm_stream_));
-      if (centred_ && rel.storage == FZ_BF16) rank1_add_local(rel, comm_stream_);
+      if (peer_rs(rel)) {
+        // every rank pulls its rows out of the peers' partials over NVLink (+ the rank-1 part), no NCCL kernel involved
+        TypeRec& Ti = *types_[rel.ti];
+        TypeRec& Tj = *types_[rel.tj];
+        signal_arrive<<<1, 32, 0, st>>>(peer_flag_ptrs_, world_, rank_, (int)rels_.size(), (int)r, peer_epoch_);
+        CUDA_OK(cudaEventRecord(ev_sig_, st));
+        CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_sig_, 0));
+        const long long n_vec = Tj.rows_loc * (Ti.k / 4);
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(4ll * sm_count_, (n_vec + 255) / 256));
+        pull_reduce<<<grid, 256, 0, comm_stream_>>>(peer_B_[r], peer_flag_ptrs_, rel.Bloc.template as<float>(), Tj.row0, Tj.rows_loc, Ti.k,
+                                                    centred_ ? rel.colsum.template as<float>() : nullptr,
+                                                    centred_ ? Ti.centre.template as<float>() : nullptr, peer_flag_ptrs_.arrive[rank_],
+                                                    peer_done_.template as<unsigned int>() + r, world_, rank_, (int)rels_.size(), (int)r,
+                                                    peer_epoch_);
+        launches += 2;
+        CUDA_OK(cudaGetLastError());
+      } else {
+        CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_rel_[r], 0));          // this relation's B partial is complete
+        NCCL_OK(nc.ReduceScatter(rel.B.p, rel.Bloc.p, (size_t)types_[rel.tj]->m_loc * types_[rel.ti]->k, dt, ncclSum, comm_, comm_stream_));
+        if (centred_ && rel.storage == FZ_BF16) rank1_add_local(rel, comm_stream_);
+      }
       if (corr_deferred()) {      // the correction of M reads this rank's reduce-scattered rows of B
         cudaStream_t fin = use_aux_ ? aux_ : st;
         CUDA_OK(cudaEventRecord(ev_rs_[r], comm_stream_));
@@ -807,6 +840,110 @@ class Engine : public EngineBase {
                            ncclFloat64, ncclSum, comm_, comm_stream_));
     CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
     CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));                           // every reduce-scatter and the all-reduce have landed
+  }
+  bool peer_rs(const RelRec& r) const { return peer_mode_ == 1 && !r.theta && r.storage == FZ_BF16 && kDT == FZ_F32 && (types_[r.ti]->k % 4) == 0; }
+  // Map every rank's B partial buffers and flag arrays into this rank (once, at the first sharded iteration; collective).
+  // Ranks in other processes are reached through CUDA IPC handles, ranks in this process through peer access; the handles
+  // travel through the communicator itself (one all-gather).  Any failure on any rank leaves every rank on NCCL's reduce-scatter.
+  void peer_setup(cudaStream_t st) {
+    peer_mode_ = 0;
+    const char* env = getenv("FZ_PEER_RS");
+    int want = (env == nullptr || env[0] != '0') ? 1 : 0;
+    if (world_ > kMaxPeers || kDT != FZ_F32) want = 0;
+    const int n_rel = (int)rels_.size();
+    struct Entry {
+      long long pid;
+      int device, ok;
+      unsigned long long ptr[2];
+      cudaIpcMemHandle_t handle[2];
+    };
+    // slot 0: flags, slot 1 + r: relation r's partial
+    const size_t per_rank = sizeof(Entry) * (size_t)(1 + n_rel);
+    std::vector<Entry> mine((size_t)(1 + n_rel));
+    memset(mine.data(), 0, per_rank);
+    if (want) {
+      peer_flags_.alloc((size_t)2 * world_ * n_rel * 8);
+      peer_done_.alloc((size_t)std::max(1, n_rel) * 4);
+      ev_sig_ = nullptr;
+      CUDA_OK(cudaEventCreateWithFlags(&ev_sig_, cudaEventDisableTiming));
+    }
+    for (int s = 0; s <= n_rel; ++s) {
+      Entry& e = mine[(size_t)s];
+      e.pid = (long long)getpid();
+      e.device = device_;
+      void* q = (s == 0) ? peer_flags_.p : rels_[(size_t)(s - 1)]->B.p;
+      e.ok = (want && q != nullptr) ? 1 : 0;
+      e.ptr[0] = (unsigned long long)(uintptr_t)q;
+      if (e.ok && cudaIpcGetMemHandle(&e.handle[0], q) != cudaSuccess) { cudaGetLastError(); e.ok = 0; }
+    }
+    DevBuf xchg;
+    xchg.alloc(per_rank * (size_t)world_);
+    CUDA_OK(cudaMemcpyAsync((char*)xchg.p + per_rank * (size_t)rank_, mine.data(), per_rank, cudaMemcpyHostToDevice, st));
+    all_gather_on(xchg.p, per_rank, ncclChar, st);
+    std::vector<Entry> all((size_t)(1 + n_rel) * (size_t)world_);
+    CUDA_OK(cudaMemcpyAsync(all.data(), xchg.p, per_rank * (size_t)world_, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    int ok = want;
+    peer_B_.assign((size_t)n_rel, PeerPtrs());
+    for (int p = 0; p < world_ && ok; ++p) {
+      for (int s = 0; s <= n_rel && ok; ++s) {
+        const Entry& e = all[(size_t)p * (1 + n_rel) + s];
+        if (s > 0 && rels_[(size_t)(s - 1)]->theta) continue;
+        if (!e.ok) { ok = 0; break; }
+        void* q = nullptr;
+        if (p == rank_) q = (void*)(uintptr_t)e.ptr[0];
+        else if (e.pid == (long long)getpid()) {          // same process: plain peer access to the other handle's device
+          int can = 0;
+          if (cudaDeviceCanAccessPeer(&can, device_, e.device) != cudaSuccess || !can) { ok = 0; break; }
+          cudaError_t pe = cudaDeviceEnablePeerAccess(e.device, 0);
+          if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; break; }
+          cudaGetLastError();
+          q = (void*)(uintptr_t)e.ptr[0];
+        } else {
+          if (cudaIpcOpenMemHandle(&q, e.handle[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+          peer_opened_.push_back(q);
+        }
+        if (s == 0) {
+          peer_flag_ptrs_.arrive[p] = (unsigned long long*)q;
+          peer_flag_ptrs_.consumed[p] = (unsigned long long*)q + (size_t)world_ * n_rel;
+        } else {
+          peer_B_[(size_t)(s - 1)].B[p] = (const float*)q;
+        }
+      }
+    }
+    // every rank must agree: the minimum of the local verdicts
+    DevBuf flag;
+    flag.alloc(8);
+    const double mine_ok = ok ? 1.0 : 0.0;
+    CUDA_OK(cudaMemcpyAsync(flag.p, &mine_ok, 8, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaEventRecord(ev_c0_, st));
+    CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
+    NCCL_OK(nccl_api().AllReduce(flag.p, flag.p, 1, ncclFloat64, ncclMin, comm_, comm_stream_));
+    CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
+    CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));
+    double all_ok = 0.0;
+    CUDA_OK(cudaMemcpyAsync(&all_ok, flag.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    peer_mode_ = (all_ok > 0.5) ? 1 : 0;
+    if (const char* gl = getenv("FZ_GATE_LOG"))
+      if (gl[0] == '1') fprintf(stderr, "[fz peer] rank %d: reduce-scatter over %s\n", rank_, peer_mode_ ? "NVLink peer memory (pull)" : "NCCL");
+  }
+  // the B partial of relation r is (re)started at zero: only once every peer has pulled last iteration's from it
+  void zero_partial(RelRec& r, cudaStream_t st) {
+    if (peer_rs(r) && peer_epoch_ > 0) {
+      const int rel = rel_index(r);
+      const long long n_vec = (long long)(r.B.bytes / 16);
+      zero_when_consumed<<<(unsigned)std::min<long long>(2 * sm_count_, (n_vec + 255) / 256), 256, 0, st>>>(
+          (float4*)r.B.p, n_vec, peer_flag_ptrs_.consumed[rank_], world_, (int)rels_.size(), rel, peer_epoch_ - 1);
+      ++launches;
+    } else {
+      CUDA_OK(cudaMemsetAsync(r.B.p, 0, r.B.bytes, st));
+    }
+  }
+  int rel_index(const RelRec& r) const {
+    for (size_t i = 0; i < rels_.size(); ++i)
+      if (rels_[i].get() == &r) return (int)i;
+    return -1;
   }
   void wait_gathers(cudaStream_t st) {
     for (size_t t = 0; t < gather_pending_.size(); ++t)
@@ -1416,7 +1553,7 @@ class Engine : public EngineBase {
   }
   // in place: this rank's `count_per_rank` elements sit at offset rank * count_per_rank of `buf`
   void all_gather_on(void* buf, size_t count_per_rank, ncclDataType_t dt, cudaStream_t st) {
-    const size_t es = (dt == ncclFloat64) ? 8 : 4;
+    const size_t es = (dt == ncclFloat64) ? 8 : (dt == ncclChar ? 1 : 4);
     CUDA_OK(cudaEventRecord(ev_c0_, st));
     CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
     NCCL_OK(nccl_api().AllGather((const char*)buf + (size_t)rank_ * count_per_rank * es, buf, count_per_rank, dt, comm_, comm_stream_));
@@ -1974,8 +2111,8 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
     rank1_init<<<nblk(Tj.n_pad * Ti.k, 256), 256, 0, st>>>(r.B.template as<float>(), Ti.k, Tj.n_pad, r.cols, Ti.k, r.colsum.template as<float>(),
                                                            Ti.centre.template as<float>());
     ++launches;
-  } else {   // (sharded with its own communicator: the rank-1 part goes onto the reduce-scattered rows instead, rank1_add_local)
-    CUDA_OK(cudaMemsetAsync(r.B.p, 0, r.B.bytes, st));
+  } else {   // (sharded with its own communicator: the rank-1 part goes onto the reduce-scattered rows instead)
+    zero_partial(r, st);
   }
   if (p.a_atomic) CUDA_OK(cudaMemsetAsync(r.A.p, 0, (size_t)r.rows_loc * Tj.k * sizeof(float), st));
   dim3 grid(pairs, splits);
