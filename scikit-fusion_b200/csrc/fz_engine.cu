@@ -812,12 +812,13 @@ class Engine : public EngineBase {
         CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_sig_, 0));
         const long long n_vec = Tj.rows_loc * (Ti.k / 4);
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(4ll * sm_count_, (n_vec + 255) / 256));
+        wait_arrive<<<1, 32, 0, comm_stream_>>>(peer_flag_ptrs_.arrive[rank_], world_, (int)rels_.size(), (int)r, peer_epoch_);
         pull_reduce<<<grid, 256, 0, comm_stream_>>>(peer_B_[r], peer_flag_ptrs_, rel.Bloc.template as<float>(), Tj.row0, Tj.rows_loc, Ti.k,
                                                     centred_ ? rel.colsum.template as<float>() : nullptr,
                                                     centred_ ? Ti.centre.template as<float>() : nullptr, peer_flag_ptrs_.arrive[rank_],
                                                     peer_done_.template as<unsigned int>() + r, world_, rank_, (int)rels_.size(), (int)r,
                                                     peer_epoch_);
-        launches += 2;
+        launches += 3;
         CUDA_OK(cudaGetLastError());
       } else {
         CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_rel_[r], 0));          // this relation's B partial is complete

@@ -60,6 +60,12 @@ __global__ void signal_arrive(PeerFlags f, int world, int rank, int n_rel, int r
   st_release_sys(f.arrive[p] + (size_t)rank * n_rel + rel, epoch);
 }
 
+// Wait (one tiny block: it co-resides with anything, so no SM is held while the ranks' skew is being waited out) until every
+// rank's partial of relation `rel` for `epoch` has arrived; the wide pull kernel is launched behind it on the same stream.
+__global__ void wait_arrive(const unsigned long long* __restrict__ arrive_mine, int world, int n_rel, int rel, unsigned long long epoch) {
+  if (threadIdx.x < world) wait_flag(arrive_mine + (size_t)threadIdx.x * n_rel + rel, epoch);
+}
+
 // B <- 0 once every peer has consumed the partial of the previous iteration (epoch_prev; 0 on the first)
 __global__ void __launch_bounds__(256)
 zero_when_consumed(float4* __restrict__ B, long long n_vec, const unsigned long long* __restrict__ consumed_mine, int world, int n_rel,
@@ -76,6 +82,7 @@ __global__ void __launch_bounds__(256)
 pull_reduce(PeerPtrs src, PeerFlags f, float* __restrict__ Bloc, long long row0, long long rows, int k, const float* __restrict__ colsum,
             const float* __restrict__ centre, const unsigned long long* __restrict__ arrive_mine, unsigned int* __restrict__ done_ctr,
             int world, int rank, int n_rel, int rel, unsigned long long epoch) {
+  // (the arrivals were waited for by wait_arrive, launched in front of this kernel; the check below is then a single load)
   if (threadIdx.x < world) wait_flag(arrive_mine + (size_t)threadIdx.x * n_rel + rel, epoch);
   __syncthreads();
   const int kv = k >> 2;

@@ -21,12 +21,16 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-def test_sharded_fit_under_torchrun_matches_the_oracle():
+@pytest.mark.parametrize("peer_rs", ["1", "0"])
+def test_sharded_fit_under_torchrun_matches_the_oracle(peer_rs):
+    """peer_rs = 1: the B partials are exchanged by the engine's pull kernel over NVLink peer memory (CUDA IPC between the two
+    processes); 0: by NCCL's reduce-scatter.  Same parity bar either way."""
     if _gpus() < 2:
         pytest.skip("needs two GPUs")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "run_sharded_nccl_check.py")],
-                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+                         capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, FZ_PEER_RS=peer_rs, FZ_GATE_LOG="1"))
+    assert ("reduce-scatter over NVLink peer memory" in out.stderr) == (peer_rs == "1"), out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("sharded NCCL check")]
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert len(lines) == 8 and all(l.endswith("PASS") for l in lines), "\n".join(lines)
