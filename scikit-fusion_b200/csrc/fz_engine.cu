@@ -497,7 +497,7 @@ class Engine : public EngineBase {
       r->ld = ld;
       r->borrowed = true;
     } else {
-      const int64_t ldo = (storage == FZ_BF16) ? ((r->cols + 7) / 8) * 8 : r->cols;
+      const int64_t ldo = (storage == FZ_BF16) ? ((r->cols + 63) / 64) * 64 : r->cols;   // bf16 rows pitched to 128 bytes (one L2 line per TMA box row)
       r->own.alloc((size_t)std::max<int64_t>(1, r->rows_loc) * ldo * dtype_size(storage));
       copy_in(data, ld, src, mem, r->own.p, ldo, storage, r->rows_loc, r->cols, st);
       r->data = r->own.p;
