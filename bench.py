@@ -477,6 +477,7 @@ def e2e_leg(args, torch, dist, fzd, _capi, R_dev, G0, types, sizes, ranks, world
     h2d = need + sum(g.nbytes for g in G0.values())
     d2h = sum(g.nbytes for g in G.values()) + sum(m.nbytes for v in S.values() for m in v)
     host.clear()
+    h = None
     gc.collect()
     try:       # hand the pinned staging buffers back to the OS: the CPU arm that follows needs the host memory
         torch._C._host_emptyCache()
