@@ -36,7 +36,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// spin (with back-off and a ~10 s watchdog: a flag that never comes is a protocol bug or a dead peer -- trap, do not hang)
+// spin (with back-off and a ~60 s watchdog: a flag that never comes is a protocol bug or a dead peer -- trap, do not hang)
 __device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long epoch) {
   if (ld_acquire_sys(p) >= epoch) return;
   unsigned long long t0;
@@ -47,7 +47,7 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned 
     if ((spins & 0xFFFu) == 0) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 10000000000ull) __trap();
+      if (t1 - t0 > 60000000000ull) __trap();
     }
   }
 }
