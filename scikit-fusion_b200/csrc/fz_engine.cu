@@ -339,6 +339,39 @@ class Engine : public EngineBase {
   // the products of the CURRENT factors are already in the buffers (fz_objective ran them for its trace form): the next
   // iteration starts from them instead of streaming the relations again
   bool products_valid_ = false;
+  // FZ_TIMELINE=1 (studies): CUDA events at the phase boundaries of every sharded iteration on the caller's stream; the mean
+  // duration of each phase is printed when the handle is destroyed
+  bool timeline_ = false;
+  std::vector<std::vector<cudaEvent_t>> tl_events_;     // per iteration: begin, products issued, reductions joined, exchanged, chain, updated
+  void tl_mark(cudaStream_t st, size_t it, int slot) {
+    if (!timeline_) return;
+    if (tl_events_.size() <= it) tl_events_.resize(it + 1);
+    if (tl_events_[it].size() <= (size_t)slot) tl_events_[it].resize((size_t)slot + 1, nullptr);
+    if (!tl_events_[it][(size_t)slot]) cudaEventCreate(&tl_events_[it][(size_t)slot]);
+    cudaEventRecord(tl_events_[it][(size_t)slot], st);
+  }
+  void tl_report() {
+    if (!timeline_ || tl_events_.size() < 4) return;
+    const char* names[] = {"products (issue .. last product done)", "join fp64 reductions", "exchange + all-reduce", "backbone chain", "updates + gathers + next operand forms", "to next iteration"};
+    double sum[6] = {0, 0, 0, 0, 0, 0};
+    int n = 0;
+    cudaDeviceSynchronize();
+    for (size_t it = 2; it + 1 < tl_events_.size(); ++it) {       // skip the first (two-term, set-up) iterations
+      if (tl_events_[it].size() < 6 || tl_events_[it + 1].empty()) continue;
+      bool ok = true;
+      float ms[6];
+      for (int s = 0; s < 5 && ok; ++s) ok = cudaEventElapsedTime(&ms[s], tl_events_[it][s], tl_events_[it][s + 1]) == cudaSuccess;
+      ok = ok && cudaEventElapsedTime(&ms[5], tl_events_[it][5], tl_events_[it + 1][0]) == cudaSuccess;
+      if (!ok) { cudaGetLastError(); continue; }
+      for (int s = 0; s < 6; ++s) sum[s] += ms[s];
+      ++n;
+    }
+    if (n == 0) return;
+    fprintf(stderr, "[fz timeline] rank %d, mean over %d iterations (ms):", rank_, n);
+    for (int s = 0; s < 6; ++s) fprintf(stderr, "  %s %.3f;", names[s], sum[s] / n);
+    fprintf(stderr, "\n");
+  }
+  size_t tl_it_ = 0;
   bool obj_exact_ = false;      // FZ_OBJ_EXACT=1: always the n_i x n_j form of the objective
   DevBuf rnorm2_, trace_jobs_, trace_out_;
   bool rnorm2_ready_ = false;
@@ -398,6 +431,8 @@ class Engine : public EngineBase {
  public:
   explicit Engine(int device) : device_(device) { this->device = device; }
   ~Engine() override {
+    tl_report();
+    for (auto& v : tl_events_) for (auto e : v) if (e) cudaEventDestroy(e);
     for (void* q : peer_opened_) cudaIpcCloseMemHandle(q);
     if (ev_sig_) cudaEventDestroy(ev_sig_);
     if (comm_) nccl_api().CommDestroy(comm_);
@@ -671,6 +706,7 @@ class Engine : public EngineBase {
     if (const char* nc = getenv("FZ_NO_CORR")) no_corr_ = (nc[0] == '1');
     if (const char* nm = getenv("FZ_NO_DMMA")) dmma_ = !(nm[0] == '1');
     if (const char* oe = getenv("FZ_OBJ_EXACT")) obj_exact_ = (oe[0] == '1');
+    if (const char* tl = getenv("FZ_TIMELINE")) timeline_ = (tl[0] == '1');
     if (const char* nd = getenv("FZ_DYN_SCHED")) dyn_sched_ = (nd[0] == '1') ? 1 : 0;
     sched_ctr_.alloc(64);
     if (gs_terms_ != 2) fused_ = false;
@@ -791,6 +827,8 @@ class Engine : public EngineBase {
     if (!products_valid_) sharded_products(st);
     products_valid_ = false;
     phase_update(algo, st);
+    tl_mark(st, tl_it_, 5);
+    ++tl_it_;
   }
   void sharded_products(cudaStream_t st) {
     const int algo = FZ_DFMF;
@@ -798,6 +836,7 @@ class Engine : public EngineBase {
     const ncclDataType_t dt = (kDT == FZ_F32) ? ncclFloat32 : ncclFloat64;
     if (peer_mode_ < 0) peer_setup(st);
     ++peer_epoch_;
+    tl_mark(st, tl_it_, 0);
     phase_products_begin(algo, st);
     for (size_t r = 0; r < rels_.size(); ++r) {
       phase_product_relation(algo, (int)r, st);
@@ -832,7 +871,9 @@ class Engine : public EngineBase {
         finish_M(rel, fin, /*local_rows=*/true);
       }
     }
+    tl_mark(st, tl_it_, 1);
     phase_products_end(algo, st);                                          // joins the fp64 reductions into st
+    tl_mark(st, tl_it_, 2);
     CUDA_OK(cudaEventRecord(ev_c0_, st));
     CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_c0_, 0));
     const int64_t first = pinv_done_ ? gram_count_ : 0;                    // the Gram sums went ahead (phase_products_begin)
@@ -841,6 +882,7 @@ class Engine : public EngineBase {
                            ncclFloat64, ncclSum, comm_, comm_stream_));
     CUDA_OK(cudaEventRecord(ev_c1_, comm_stream_));
     CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));                           // every reduce-scatter and the all-reduce have landed
+    tl_mark(st, tl_it_, 3);
   }
   bool peer_rs(const RelRec& r) const { return peer_mode_ == 1 && !r.theta && r.storage == FZ_BF16 && kDT == FZ_F32 && (types_[r.ti]->k % 4) == 0; }
   // Map every rank's B partial buffers and flag arrays into this rank (once, at the first sharded iteration; collective).
@@ -1055,6 +1097,7 @@ class Engine : public EngineBase {
     need_final();
     const bool dfmf = (algo == FZ_DFMF);
     run_chain(/*solve=*/true, /*scrub=*/dfmf, st);
+    if (dfmf && world_ > 1) tl_mark(st, tl_it_, 4);
     if (dfmf) {
       if (single_now_) ++n_single_; else ++n_two_;
       if (gate_check_now_) gate_decide(st);
