@@ -37,7 +37,10 @@ extern "C" {
 
 typedef struct fz_engine fz_engine;
 
-typedef enum { FZ_F64 = 0, FZ_F32 = 1, FZ_BF16 = 2, FZ_U8 = 3 } fz_dtype;
+typedef enum {
+  FZ_F64 = 0, FZ_F32 = 1, FZ_BF16 = 2, FZ_U8 = 3,
+  FZ_BF16X3 = 4   /* storage only: fp32 master + up to three bf16 planes whose sum is the fp32 value exactly */
+} fz_dtype;
 typedef enum { FZ_HOST = 0, FZ_DEVICE = 1 } fz_mem;
 typedef enum { FZ_DFMF = 0, FZ_DFMC = 1 } fz_algo;
 
@@ -82,8 +85,15 @@ int fz_group_init_end(fz_engine** engines, int n);
 int fz_add_type(fz_engine* e, int64_t n, int k);
 /* Relation between row type ti and column type tj; ti == tj declares a constraint matrix Theta_t.
  *   data        rows_local x n_tj matrix of `src` dtype (rows_local = n_ti unless sharded)
- *   storage     dtype kept on the device: FZ_F64 / FZ_F32 (SIMT fp path) or FZ_BF16 (tensor-core path,
- *               needs ld % 8 == 0 when borrowed; the engine pads its own copies)
+ *   storage     dtype kept on the device: FZ_F64 / FZ_F32 (exact CUDA-core path), FZ_BF16 (tensor-core path, the relation
+ *               rounded to bf16; rank <= 64 for the fused kernels; needs ld % 8 == 0 when borrowed, the engine pads its own
+ *               copies; constraint matrices and masked relations asked for in bf16 are kept exact in the compute dtype), or
+ *               FZ_BF16X3 (fp32 engine): the relation is kept in fp32 AND split into the bf16 planes P0 + P1 + P2 = R
+ *               (exactly; all-zero planes are dropped, so 0/1 data, ratings and small integers cost one plane).  The
+ *               streamed products run on the tensor cores once per plane, accumulating into the same outputs: no bit of R
+ *               is lost, the factor operand carries 16 bits (two bf16 terms).  Valid for masked relations (dfmc re-splits
+ *               the imputed entries every iteration), constraint matrices (Theta+ and Theta- as separate plane sets) and
+ *               any rank (ranks above 64 take the two-pass kernels over 64-column blocks of the factor)
  *   borrow      1: use the caller's buffer in place -- device memory, or (mem = FZ_HOST) PINNED host memory, which is then read
  *               over PCIe every iteration: the out-of-core mode for relations that do not fit HBM
  *   mask        optional rows_local x n_tj uint8 (non-zero = unknown entry, dfmc), NULL otherwise

@@ -8,8 +8,9 @@
 //        G_i^T R_ij G_j = G_i^T A_ij                     (S-update,  _dfmf.py:236-239)
 //        tmp1 = R_ij (G_j S^T) = A_ij S^T                 (_dfmf.py:254)
 //        tmp4 = R_ij^T (G_i S) = B_ij S                   (_dfmf.py:266)
-// bf16-stored relations take the tcgen05/TMA kernel (umma_skinny.cuh); fp32 / fp64-stored ones the exact
-// CUDA-core kernel.  The k x k chain is always fp64 (fz_chain.cuh).  There is no CPU fallback anywhere.
+// bf16-stored relations take the tcgen05/TMA kernels (umma_fused*.cuh, umma_skinny.cuh), and so do fp32 relations kept as
+// exact bf16 planes (FZ_BF16X3: constraint matrices, masked relations and ranks above 64 included); plain fp32 / fp64-stored
+// ones the exact CUDA-core kernel.  The k x k chain is always fp64 (fz_chain.cuh).  There is no CPU fallback anywhere.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -262,11 +263,13 @@ class Engine : public EngineBase {
   struct TypeRec {
     int64_t n = 0, n_pad = 0, m_loc = 0, row0 = 0, rows_loc = 0;
     int k = 0;
+    int kp = 64;             // rank padded to whole 64-column blocks: width of one term of the operand form
     DevBuf G[2];
     int cur = 0;
     bool has_factor = false;
     bool need_gs = false;
-    DevBuf Gs;               // bf16 [n_pad][terms*kKp]
+    bool gs_centred = false; // Gs currently holds the terms of G - 1 c^T (centred form) rather than of G
+    DevBuf Gs;               // bf16 [n_pad][terms*kp]
     CUtensorMap tmG;         // box {64 cols, 64 rows}   (two-pass kernels)
     CUtensorMap tmG128;      // box {64 cols, 128 rows}  (fused kernel)
     DevBuf GsT;              // bf16 [128][ldt]: transposed operand form (umma_fused_t.cuh), fused kernel v4
@@ -289,9 +292,21 @@ class Engine : public EngineBase {
     DevBuf upd_terms, upd_adds, sum_ptrs;
     int n_terms = 0, n_adds = 0;
   };
+  // bf16 planes of an fp32 matrix (FZ_BF16X3): P0 + P1 + ... = the matrix, exactly; each plane has its own TMA descriptors
+  // and is streamed like a bf16-stored relation.  n = 0: the matrix (or this sign part of it) is all zero.
+  struct PlaneSet {
+    DevBuf buf;              // [n][rows][ld] bf16
+    int n = 0;
+    int64_t ld = 0, stride = 0;
+    CUtensorMap tmX[3], tmXT[3];     // box {64 cols, 128 rows} / {64 cols, 64 rows}
+    DevBuf rowsum;           // constraint parts in the centred operand form: row sums of this part (fp32)
+  };
   struct RelRec {
     int ti = 0, tj = 0, storage = FZ_F32;
     bool theta = false, borrowed = false;
+    bool tc = false;         // streamed products on the tensor cores: bf16 storage, or fp32 master + bf16 planes (x3)
+    bool x3 = false;
+    PlaneSet pl, pl_neg;     // the relation's planes (bf16 storage: the relation itself as plane 0); constraints: Theta+ / Theta-
     void* data = nullptr;
     int64_t ld = 0, rows_loc = 0, cols = 0;
     DevBuf own;
@@ -504,12 +519,14 @@ class Engine : public EngineBase {
     TypeRec& Tj = *types_[tj];
     r->rows_loc = Ti.rows_loc;
     r->cols = Tj.n;
-    if (storage != FZ_BF16) storage = kDT;  // CUDA-core path keeps the relation in the compute dtype
+    // exact tensor-core form: fp32 master (every element-wise kernel keeps reading it) + bf16 planes built in fz_finalize
+    r->x3 = (storage == FZ_BF16X3);
+    if (r->x3 && kDT != FZ_F32) FZ_THROW(FZ_ERR_UNSUPPORTED, "bf16x3 relations need the fp32 engine");
+    if (storage != FZ_BF16) storage = kDT;  // CUDA-core path (and the x3 master) keep the relation in the compute dtype
     if (storage == FZ_BF16 && (r->theta || mask != nullptr)) storage = kDT;  // constraints / completion stay exact
     if (storage == FZ_BF16 && kDT != FZ_F32) FZ_THROW(FZ_ERR_UNSUPPORTED, "bf16 relations need the fp32 engine");
-    if (storage == FZ_BF16 && (Ti.k > kKp || Tj.k > kKp))
-      FZ_THROW(FZ_ERR_UNSUPPORTED, "tensor-core path supports rank <= %d (got %d, %d)", kKp, Ti.k, Tj.k);
     r->storage = storage;
+    r->tc = (storage == FZ_BF16) || r->x3;
     cudaStream_t st = 0;
     if (borrow && mem == FZ_HOST) {
       // Out-of-core relation: PINNED host memory used in place.  Every kernel that touches the relation (the TMA loads of the
@@ -551,8 +568,8 @@ class Engine : public EngineBase {
     else {
       Ti.row_rels.push_back(id);
       Tj.col_rels.push_back(id);
-      if (storage == FZ_BF16) { Ti.need_gs = true; Tj.need_gs = true; }
     }
+    if (r->tc) { Ti.need_gs = true; Tj.need_gs = true; }
     rels_.push_back(std::move(r));
     return id;
   }
@@ -592,6 +609,12 @@ class Engine : public EngineBase {
     const int sms = prop.multiProcessorCount;
     sm_count_ = sms;
     if (const char* nf = getenv("FZ_NO_FUSED")) fused_ = !(nf[0] == '1');
+    for (auto& t : types_) {
+      t->kp = ((t->k + kKp - 1) / kKp) * kKp;
+      // the fused kernels hold one 64-column accumulator per product: factors of rank > 64 take the two-pass kernels over
+      // 64-column blocks of the operand (umma), with the plain operand form
+      if (t->need_gs && t->k > kKp) fused_ = false;
+    }
     centred_ = (terms_ <= 0) && fused_ && kDT == FZ_F32;
     if (terms_ <= 0 && !centred_) terms_ = 2;       // the centred forms exist for the fused fp32-engine products only
     gs_terms_ = terms_ <= 0 ? 2 : terms_;
@@ -606,7 +629,7 @@ class Engine : public EngineBase {
     int64_t gate_off = small_count_;
     if (centred_ && terms_ == FZ_TERMS_AUTO) {
       for (auto& r : rels_)
-        if (!r->theta && r->storage == FZ_BF16) gate_slot_count_ += 4;
+        if (!r->theta && r->tc) gate_slot_count_ += 4;
       small_count_ += gate_slot_count_;
       gate_probe_.alloc((size_t)2 * 128 * 64 * sizeof(float));
     }
@@ -638,7 +661,7 @@ class Engine : public EngineBase {
         t.centre_chunks = (int)std::max<long long>(1, (t.n + t.centre_rows_per_chunk - 1) / t.centre_rows_per_chunk);
         t.centre_part.alloc((size_t)t.centre_chunks * t.k * 8);
       }
-      if (t.need_gs && fused_ver_ == 4 && gs_terms_ == 2 && kDT == FZ_F32) {
+      if (t.need_gs && fused_ver_ == 4 && gs_terms_ == 2 && kDT == FZ_F32 && fused_) {
         t.ldt = ((t.n_pad + 255) / 256) * 256 + 256;   // a CTA preloads 256 rows from any local row offset
         t.GsT.alloc((size_t)128 * t.ldt * 2);
         CUDA_OK(cudaMemset(t.GsT.p, 0, t.GsT.bytes));
@@ -647,16 +670,31 @@ class Engine : public EngineBase {
           FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
       }
       if (t.need_gs) {
-        t.Gs.alloc((size_t)t.n_pad * gs_terms_ * kKp * 2);
+        t.Gs.alloc((size_t)t.n_pad * gs_terms_ * t.kp * 2);
         std::string e;
-        if (!make_tmap_bf16_2d(&t.tmG, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 64, &e) ||
-            !make_tmap_bf16_2d(&t.tmG128, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 128, &e))
+        if (!make_tmap_bf16_2d(&t.tmG, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)gs_terms_ * t.kp, (uint64_t)gs_terms_ * t.kp, 64, 64, &e) ||
+            !make_tmap_bf16_2d(&t.tmG128, t.Gs.p, (uint64_t)t.n_pad, (uint64_t)gs_terms_ * t.kp, (uint64_t)gs_terms_ * t.kp, 64, 128, &e))
           FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
       }
     }
     for (auto& rp : rels_) {
       RelRec& r = *rp;
-      if (r.theta) continue;
+      if (r.theta) {
+        if (r.x3) {      // Theta+ and Theta- as separate plane sets (both products are non-negative sums, _dfmf.py:284-292)
+          build_planes(r, r.pl, +1, false, false);
+          build_planes(r, r.pl_neg, -1, false, false);
+          if (centred_) {      // the rank-1 parts of Theta+- G in the centred operand form
+            for (PlaneSet* ps : {&r.pl, &r.pl_neg}) {
+              if (ps->n == 0 || r.rows_loc <= 0) continue;
+              ps->rowsum.alloc((size_t)r.rows_loc * sizeof(float));
+              row_sums_part<<<nblk(r.rows_loc, 8), 256>>>((const float*)r.data, r.ld, r.rows_loc, r.cols, ps == &r.pl ? +1 : -1,
+                                                         ps->rowsum.template as<float>());
+            }
+            CUDA_OK(cudaDeviceSynchronize());
+          }
+        }
+        continue;
+      }
       TypeRec& Ti = *types_[r.ti];
       TypeRec& Tj = *types_[r.tj];
       r.M_raw = small_.template as<double>() + off;
@@ -666,7 +704,7 @@ class Engine : public EngineBase {
       if (world_ > 1) r.Bloc.alloc((size_t)Tj.m_loc * Ti.k * sizeof(T));
       r.m_rows_per_chunk = Ti.gram_rows_per_chunk;
       r.m_chunks = Ti.gram_chunks;
-      if (centred_ && r.storage == FZ_BF16) {
+      if (centred_ && r.tc) {
         r.corr_rows_per_chunk = (int)std::max<int64_t>(64, (Tj.n_pad + 2 * sms - 1) / (2 * sms));
         r.corr_rows_per_chunk = ((r.corr_rows_per_chunk + 15) / 16) * 16;
         r.corr_chunks = (int)std::max<int64_t>(1, (Tj.n_pad + r.corr_rows_per_chunk - 1) / r.corr_rows_per_chunk);
@@ -681,18 +719,29 @@ class Engine : public EngineBase {
       r.W4.alloc((size_t)Ti.k * Tj.k * sizeof(T));
       const int km = std::max(Ti.k, Tj.k);
       r.work.alloc((size_t)6 * km * km * 8);
-      if (r.storage == FZ_BF16) {
+      if (r.x3) {
+        // masked relations keep all three planes: dfmc writes arbitrary fp32 values into the unknown entries
+        build_planes(r, r.pl, 0, /*all_three=*/r.mask != nullptr, /*keep_one=*/true);
+        r.tmX = r.pl.tmX[0];
+        r.tmXT = r.pl.tmXT[0];
+      }
+      if (r.tc) {
         std::string e;
-        bool ok = make_tmap_bf16_2d(&r.tmX, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols, (uint64_t)r.ld, 64, 128, &e) &&
-                  make_tmap_bf16_2d(&r.tmXT, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols, (uint64_t)r.ld, 64, 64, &e);
-        if (!ok) FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+        if (!r.x3) {
+          bool ok = make_tmap_bf16_2d(&r.tmX, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols, (uint64_t)r.ld, 64, 128, &e) &&
+                    make_tmap_bf16_2d(&r.tmXT, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols, (uint64_t)r.ld, 64, 64, &e);
+          if (!ok) FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+          r.pl.n = 1;            // the relation itself is its only plane
+          r.pl.tmX[0] = r.tmX;
+          r.pl.tmXT[0] = r.tmXT;
+        }
         // reduce target of the fused kernel's TMA flush (fp32, box 32 x 32, 128B swizzle)
         if (kDT == FZ_F32 && (Ti.k % 4) == 0 && Ti.k >= 32)
           r.has_tmB = make_tmap_f32_2d(&r.tmB, r.B.p, (uint64_t)Tj.n_pad, (uint64_t)Ti.k, (uint64_t)Ti.k, 32, 32, &e);
         if (kDT == FZ_F32 && centred_ && (Tj.k % 4) == 0 && Tj.k >= 32 && r.rows_loc >= 32)   // A reduce target of the single-term kernel
           r.has_tmA = make_tmap_f32_2d(&r.tmA, r.A.p, (uint64_t)r.rows_loc, (uint64_t)Tj.k, (uint64_t)Tj.k, 32, 32, &e);
         // v4 boxes are {64, 256} on the relation and {16, 64} on B: relations smaller than a box keep the v3 kernel
-        if (fused_ver_ == 4 && kDT == FZ_F32 && r.rows_loc >= 256 && r.cols >= 64 && Ti.GsT.p != nullptr && Tj.GsT.p != nullptr) {
+        if (fused_ver_ == 4 && kDT == FZ_F32 && !r.x3 && r.rows_loc >= 256 && r.cols >= 64 && Ti.GsT.p != nullptr && Tj.GsT.p != nullptr) {
           r.v4_ok = make_tmap_2d(&r.tmX256, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, r.data, (uint64_t)r.rows_loc, (uint64_t)r.cols,
                                  (uint64_t)r.ld, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B, &e);
           if (r.v4_ok && (Ti.k % 4) == 0 && Tj.n_pad >= 64)      // one {64 k, 64 rows} reduce per chunk (flush mode 2)
@@ -862,7 +911,7 @@ class Engine : public EngineBase {
       } else {
         CUDA_OK(cudaStreamWaitEvent(comm_stream_, ev_rel_[r], 0));          // this relation's B partial is complete
         NCCL_OK(nc.ReduceScatter(rel.B.p, rel.Bloc.p, (size_t)types_[rel.tj]->m_loc * types_[rel.ti]->k, dt, ncclSum, comm_, comm_stream_));
-        if (centred_ && rel.storage == FZ_BF16) rank1_add_local(rel, comm_stream_);
+        if (centred_ && rel.tc) rank1_add_local(rel, comm_stream_);
       }
       if (corr_deferred()) {      // the correction of M reads this rank's reduce-scattered rows of B
         cudaStream_t fin = use_aux_ ? aux_ : st;
@@ -884,7 +933,7 @@ class Engine : public EngineBase {
     CUDA_OK(cudaStreamWaitEvent(st, ev_c1_, 0));                           // every reduce-scatter and the all-reduce have landed
     tl_mark(st, tl_it_, 3);
   }
-  bool peer_rs(const RelRec& r) const { return peer_mode_ == 1 && !r.theta && r.storage == FZ_BF16 && kDT == FZ_F32 && (types_[r.ti]->k % 4) == 0; }
+  bool peer_rs(const RelRec& r) const { return peer_mode_ == 1 && !r.theta && r.tc && fused_ && kDT == FZ_F32 && (types_[r.ti]->k % 4) == 0; }
   // Map every rank's B partial buffers and flag arrays into this rank (once, at the first sharded iteration; collective).
   // Ranks in other processes are reached through CUDA IPC handles, ranks in this process through peer access; the handles
   // travel through the communicator itself (one all-gather).  Any failure on any rank leaves every rank on NCCL's reduce-scatter.
@@ -1011,6 +1060,7 @@ class Engine : public EngineBase {
             mask_zero<T><<<nblk(rp->rows_loc * rp->cols, 256), 256, 0, st>>>((T*)rp->data, rp->ld, rp->mask, rp->mask_ld,
                                                                               rp->rows_loc, rp->cols);
             ++launches;
+            resplit_masked(*rp, st);
           }
         dfmc_started_ = true;
       }
@@ -1069,7 +1119,7 @@ class Engine : public EngineBase {
     (void)algo;
     RelRec& r = relation(rel);
     if (r.theta) return;
-    if (centred_ && comm_ && r.storage == FZ_BF16) ensure_sums(r, st);     // holds a collective: every rank, rows or not
+    if (centred_ && comm_ && r.tc) ensure_sums(r, st);     // holds a collective: every rank, rows or not
     if (!product_AB_fused(r, st)) {
       product_A(r, st);
       product_B(r, st);
@@ -1116,6 +1166,7 @@ class Engine : public EngineBase {
         impute_masked<T><<<g, 256, 0, st>>>((T*)r.data, r.ld, r.mask, r.mask_ld, r.T1.template as<T>(), Tj.k, cur(Tj), Tj.k,
                                             r.rows_loc, r.cols, Tj.k);
         ++launches;
+        resplit_masked(r, st);
       }
       for (auto& rp : rels_) {
         if (rp->theta) continue;
@@ -1182,7 +1233,9 @@ class Engine : public EngineBase {
     for (size_t r = 0; r < rels_.size() && can_pair; ++r) {
       RelRec& a = *rels_[r];
       RelRec& b = *other->rels_[r];
-      can_pair = a.ti == b.ti && a.tj == b.tj && a.theta == b.theta && (a.theta || (a.storage == FZ_BF16 && a.data == b.data && a.ld == b.ld));
+      // (constraints on the tensor cores read the per-handle operand form, which a paired iteration does not build)
+      can_pair = a.ti == b.ti && a.tj == b.tj && a.theta == b.theta &&
+                 (a.theta ? (!a.tc && !b.tc) : (a.storage == FZ_BF16 && a.data == b.data && a.ld == b.ld));
     }
     check_factors();
     other->check_factors();
@@ -1222,7 +1275,7 @@ class Engine : public EngineBase {
     RelRec& r = relation(rel);
     if (ptr) *ptr = r.data;
     if (ld) *ld = r.ld;
-    if (dtype) *dtype = r.storage;
+    if (dtype) *dtype = r.x3 ? (int)FZ_BF16X3 : r.storage;      // x3: the pointer is the fp32 master
   }
   int64_t n_paired_ = 0;
   // operand forms of both runs side by side: [n_pad][128] = [bf16(G0 - c0) | bf16(G1 - c1)]
@@ -1303,15 +1356,15 @@ class Engine : public EngineBase {
       const T* W = row_role ? r.W1.template as<T>() : r.W4.template as<T>();
       gemm(cur(To), To.k, W, Tt.k, r.E.template as<T>(), Tt.k, (int)To.n, Tt.k, To.k, false, st);
       r.Cx.alloc((size_t)Tt.n * Tt.k * sizeof(T));
-      if (r.storage == FZ_BF16) {
-        r.Es.alloc((size_t)To.n * gs_terms_ * kKp * 2);
-        split_factor<T><<<nblk(To.n * kKp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(),
-                                                                To.n, To.n, Tt.k, kKp, gs_terms_);
+      if (r.tc) {
+        r.Es.alloc((size_t)To.n * gs_terms_ * Tt.kp * 2);
+        split_factor<T><<<nblk(To.n * Tt.kp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(),
+                                                                  To.n, To.n, Tt.k, Tt.kp, gs_terms_);
         ++launches;
         std::string e;
-        if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 64, &e))
+        if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n, (uint64_t)gs_terms_ * Tt.kp, (uint64_t)gs_terms_ * Tt.kp, 64, 64, &e))
           FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
-        umma(r, /*trans=*/!row_role, r.tmEs, 0, r.Cx.template as<T>(), Tt.k, (int)Tt.n, (int)To.n, Tt.k, st);
+        umma(r.pl, /*trans=*/!row_role, r.tmEs, 0, r.Cx.template as<T>(), Tt.k, (int)Tt.n, (int)To.n, Tt.k, false, st);
       } else {
         if (row_role) gemm((const T*)r.data, r.ld, r.E.template as<T>(), Tt.k, r.Cx.template as<T>(), Tt.k, (int)Tt.n, Tt.k, (int)To.n, false, st);
         else gemm_t((const T*)r.data, r.ld, r.E.template as<T>(), Tt.k, r.Cx.template as<T>(), Tt.k, (int)Tt.n, Tt.k, (int)To.n, st);
@@ -1327,7 +1380,10 @@ class Engine : public EngineBase {
     need_final();
     if (tf_target_ < 0) FZ_THROW(FZ_ERR_INVALID, "fz_transform_prepare first");
     TypeRec& Tt = *types_[tf_target_];
+    bool tc_theta = false;
+    for (int id : Tt.thetas) tc_theta = tc_theta || rels_[id]->tc;
     for (int it = 0; it < n_iters; ++it) {
+      if (tc_theta) split(Tt, st, false);      // the target factor moves every iteration: so does its operand form
       theta_products(st);
       update_type(tf_target_, 0, st);
       Tt.cur ^= 1;
@@ -1635,15 +1691,15 @@ class Engine : public EngineBase {
     const int M = (int)(row_role ? r.rows_loc : Tt.n);
     const int K = (int)(row_role ? To.n : r.rows_loc);
     if (r.rows_loc > 0) {
-      if (r.storage == FZ_BF16) {
-        r.Es.alloc((size_t)To.n_pad * gs_terms_ * kKp * 2);
-        split_factor<T><<<nblk(To.n_pad * kKp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(), To.n, To.n_pad,
-                                                                    Tt.k, kKp, gs_terms_);
+      if (r.tc) {
+        r.Es.alloc((size_t)To.n_pad * gs_terms_ * Tt.kp * 2);
+        split_factor<T><<<nblk(To.n_pad * Tt.kp, 256), 256, 0, st>>>(r.E.template as<T>(), Tt.k, r.Es.template as<__nv_bfloat16>(), To.n, To.n_pad,
+                                                                      Tt.k, Tt.kp, gs_terms_);
         ++launches;
         std::string e;
-        if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n_pad, (uint64_t)gs_terms_ * kKp, (uint64_t)gs_terms_ * kKp, 64, 64, &e))
+        if (!make_tmap_bf16_2d(&r.tmEs, r.Es.p, (uint64_t)To.n_pad, (uint64_t)gs_terms_ * Tt.kp, (uint64_t)gs_terms_ * Tt.kp, 64, 64, &e))
           FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
-        umma(r, /*trans=*/!row_role, r.tmEs, row_role ? 0 : To.row0, C, Tt.k, M, K, Tt.k, st);
+        umma(r.pl, /*trans=*/!row_role, r.tmEs, row_role ? 0 : To.row0, C, Tt.k, M, K, Tt.k, false, st);
       } else {
         const T* W = r.E.template as<T>() + (row_role ? 0 : To.row0 * Tt.k);
         if (row_role) gemm((const T*)r.data, r.ld, W, Tt.k, C, Tt.k, M, Tt.k, K, false, st);
@@ -1732,8 +1788,59 @@ class Engine : public EngineBase {
     cudaFuncSetAttribute(trace_objective, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
     cudaFuncSetAttribute(backbone_chain<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
   }
-  // tensor-core product of a bf16 relation with a split factor:  C (M x k) = op(R) * Gs[g_row0 + ., :]
-  void umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g_row0, T* C, int64_t ldc, int M, int K, int k, cudaStream_t st);
+  // tensor-core product of a relation (all its bf16 planes) with a split factor:  C (M x k) (+)= op(R) * Gs[g_row0 + ., :]
+  // -- one launch per plane and per 64-column block of the factor, accumulating into C
+  void umma(const PlaneSet& ps, bool trans, const CUtensorMap& tg, int64_t g_row0, T* C, int64_t ldc, int M, int K, int k,
+            bool accumulate, cudaStream_t st);
+
+  // FZ_BF16X3: split the fp32 master of a relation (part 0) or one sign part of a constraint matrix (+1 / -1) into its bf16
+  // planes.  A first pass finds out how many planes hold anything (0/1 data, ratings, small integers: one), so only those are
+  // allocated and streamed.  Set-up step: synchronises.
+  void build_planes(RelRec& r, PlaneSet& ps, int part, bool all_three, bool keep_one) {
+    if (kDT != FZ_F32) FZ_THROW(FZ_ERR_UNSUPPORTED, "bf16 planes need the fp32 engine");
+    DevBuf need;
+    need.alloc(4 * sizeof(unsigned int));
+    unsigned int h[4] = {0, 0, 0, 0};
+    if (r.rows_loc > 0) {
+      planes_needed<<<nblk(r.rows_loc * r.cols, 256), 256>>>((const float*)r.data, r.ld, r.rows_loc, r.cols, part,
+                                                             need.template as<unsigned int>());
+      ++launches;
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaMemcpy(h, need.p, sizeof(h), cudaMemcpyDeviceToHost));
+    }
+    if (h[3]) FZ_THROW(FZ_ERR_INVALID, "a relation with non-finite entries cannot be split into bf16 planes (fill the unknown values first)");
+    int n = h[2] ? 3 : (h[1] ? 2 : (h[0] ? 1 : 0));
+    if (all_three) n = 3;
+    if (keep_one && n == 0) n = 1;
+    ps.n = n;
+    if (n == 0) return;
+    const int64_t rows = std::max<int64_t>(1, r.rows_loc);
+    ps.ld = ((r.cols + 63) / 64) * 64;              // rows pitched to 128 bytes, like the engine's own bf16 copies
+    ps.stride = rows * ps.ld;
+    ps.buf.alloc((size_t)n * ps.stride * 2);        // zeroed: pad columns and absent rows read as 0
+    if (r.rows_loc > 0) {
+      split_planes<<<nblk(r.rows_loc * r.cols, 256), 256>>>((const float*)r.data, r.ld, ps.buf.template as<__nv_bfloat16>(), ps.ld,
+                                                            ps.stride, n, r.rows_loc, r.cols, part);
+      ++launches;
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaDeviceSynchronize());
+    }
+    std::string e;
+    for (int q = 0; q < n; ++q) {
+      const __nv_bfloat16* base = ps.buf.template as<__nv_bfloat16>() + (size_t)q * ps.stride;
+      if (!make_tmap_bf16_2d(&ps.tmX[q], base, (uint64_t)rows, (uint64_t)r.cols, (uint64_t)ps.ld, 64, 128, &e) ||
+          !make_tmap_bf16_2d(&ps.tmXT[q], base, (uint64_t)rows, (uint64_t)r.cols, (uint64_t)ps.ld, 64, 64, &e))
+        FZ_THROW(FZ_ERR_CUDA, "%s", e.c_str());
+    }
+  }
+  // dfmc rewrote the unknown entries of the master (mask_zero / impute_masked): bring the planes up to date there
+  void resplit_masked(RelRec& r, cudaStream_t st) {
+    if (!r.x3 || r.mask == nullptr || r.rows_loc <= 0) return;
+    split_planes_masked<<<nblk(r.rows_loc * r.cols, 256), 256, 0, st>>>((const float*)r.data, r.ld, r.mask, r.mask_ld,
+                                                                        r.pl.buf.template as<__nv_bfloat16>(), r.pl.ld, r.pl.stride, r.pl.n,
+                                                                        r.rows_loc, r.cols);
+    ++launches;
+  }
 
   void split(TypeRec& t, cudaStream_t st, bool centred = false, const T* G = nullptr) {
     if (G == nullptr) G = cur(t);
@@ -1744,11 +1851,12 @@ class Engine : public EngineBase {
       launches += 2;
       centre = t.centre.template as<float>();
     }
-    split_factor<T><<<nblk(t.n_pad * kKp, 256), 256, 0, st>>>(G, t.k, t.Gs.template as<__nv_bfloat16>(), t.n, t.n_pad, t.k, kKp,
-                                                               gs_terms_, centre);
+    split_factor<T><<<nblk(t.n_pad * t.kp, 256), 256, 0, st>>>(G, t.k, t.Gs.template as<__nv_bfloat16>(), t.n, t.n_pad, t.k, t.kp,
+                                                                gs_terms_, centre);
     ++launches;
     t.hi_ptr = t.Gs.template as<__nv_bfloat16>();
-    t.hi_ld = (long long)gs_terms_ * kKp;
+    t.hi_ld = (long long)gs_terms_ * t.kp;
+    t.gs_centred = centred;
     if (t.GsT.p != nullptr) {
       split_factor_t<T><<<nblk(t.n_pad, 64), 256, 0, st>>>(cur(t), t.k, t.GsT.template as<__nv_bfloat16>(), t.ldt, t.n, t.ldt, t.k);
       ++launches;
@@ -1777,7 +1885,7 @@ class Engine : public EngineBase {
   void product_A(RelRec& r, cudaStream_t st) {   // A = R G_j   (local rows of type i)
     TypeRec& Tj = *types_[r.tj];
     if (r.rows_loc <= 0) return;
-    if (r.storage == FZ_BF16) umma(r, false, Tj.tmG, 0, r.A.template as<T>(), Tj.k, (int)r.rows_loc, (int)r.cols, Tj.k, st);
+    if (r.tc) umma(r.pl, false, Tj.tmG, 0, r.A.template as<T>(), Tj.k, (int)r.rows_loc, (int)r.cols, Tj.k, false, st);
     else gemm((const T*)r.data, r.ld, cur(Tj), Tj.k, r.A.template as<T>(), Tj.k, (int)r.rows_loc, Tj.k, (int)r.cols, false, st);
   }
   void product_B(RelRec& r, cudaStream_t st) {   // B = R^T G_i[local rows]   (all rows of type j)
@@ -1787,7 +1895,7 @@ class Engine : public EngineBase {
       CUDA_OK(cudaMemsetAsync(r.B.p, 0, r.B.bytes, st));
       return;
     }
-    if (r.storage == FZ_BF16) umma(r, true, Ti.tmG, Ti.row0, r.B.template as<T>(), Ti.k, (int)r.cols, (int)r.rows_loc, Ti.k, st);
+    if (r.tc) umma(r.pl, true, Ti.tmG, Ti.row0, r.B.template as<T>(), Ti.k, (int)r.cols, (int)r.rows_loc, Ti.k, false, st);
     else gemm_t((const T*)r.data, r.ld, cur(Ti) + Ti.row0 * Ti.k, Ti.k, r.B.template as<T>(), Ti.k, (int)r.cols, Ti.k, (int)r.rows_loc, st);
   }
   // A and B from ONE stream of a bf16 relation (umma_fused.cuh).  Returns false when not applicable.
@@ -1811,7 +1919,7 @@ class Engine : public EngineBase {
     TypeRec& Ti = *types_[r.ti];
     TypeRec& Tj = *types_[r.tj];
     int chunks = r.m_chunks;
-    if (single_now_ && !no_corr_ && r.storage == FZ_BF16) { corr_M(r, st, local_rows); chunks += r.corr_chunks; }
+    if (single_now_ && !no_corr_ && r.tc) { corr_M(r, st, local_rows); chunks += r.corr_chunks; }
     reduce_partials<<<nblk((long long)Ti.k * Tj.k, 32), kRedThreads, 0, st>>>(r.M_part.template as<double>(), r.M_raw, chunks,
                                                                        (long long)Ti.k * Tj.k);
     ++launches;
@@ -1864,13 +1972,15 @@ class Engine : public EngineBase {
   void ensure_sums(RelRec& r, cudaStream_t st) {
     if (r.sums_ready) return;
     if (r.rows_loc > 0) {
-      row_sums<__nv_bfloat16><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, r.rowsum.template as<float>());
+      if (r.storage == FZ_BF16) row_sums<__nv_bfloat16><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, r.rowsum.template as<float>());
+      else row_sums<T><<<nblk(r.rows_loc, 8), 256, 0, st>>>((const T*)r.data, r.ld, r.rows_loc, r.cols, r.rowsum.template as<float>());     // x3: the fp32 master
       const int chunks = (int)std::min<int64_t>(128, std::max<int64_t>(1, (r.rows_loc + 127) / 128));
       const int64_t rpc = (r.rows_loc + chunks - 1) / chunks;
       DevBuf part;
       part.alloc((size_t)chunks * r.cols * 8, false);
       dim3 g(nblk(r.cols, 256), chunks);
-      col_sums_partial<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, rpc, part.template as<double>());
+      if (r.storage == FZ_BF16) col_sums_partial<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)r.data, r.ld, r.rows_loc, r.cols, rpc, part.template as<double>());
+      else col_sums_partial<T><<<g, 256, 0, st>>>((const T*)r.data, r.ld, r.rows_loc, r.cols, rpc, part.template as<double>());
       finish_col_sums<<<nblk(r.cols, 256), 256, 0, st>>>(part.template as<double>(), r.colsum.template as<float>(), chunks, r.cols);
       launches += 3;
       CUDA_OK(cudaGetLastError());
@@ -1896,14 +2006,21 @@ class Engine : public EngineBase {
       for (int id : t.thetas) {
         RelRec& r = *rels_[id];
         if (r.rows_loc <= 0) continue;
-        dim3 g(nblk(r.rows_loc, kGemmBM), nblk(t.k, kGemmBN));
-        gemm_simt<T, T, false, true><<<g, 256, 0, st>>>((const T*)r.data, r.ld, cur(t), t.k, t.thP.template as<T>(),
-                                                         t.thN.template as<T>(), t.k, (int)r.rows_loc, t.k, (int)r.cols, first ? 0 : 1);
-        ++launches;
+        if (r.tc) {
+          theta_tc(t, r, first, st);      // bf16 planes of Theta+ / Theta- on the tensor cores
+        } else {
+          dim3 g(nblk(r.rows_loc, kGemmBM), nblk(t.k, kGemmBN));
+          gemm_simt<T, T, false, true><<<g, 256, 0, st>>>((const T*)r.data, r.ld, cur(t), t.k, t.thP.template as<T>(),
+                                                           t.thN.template as<T>(), t.k, (int)r.rows_loc, t.k, (int)r.cols, first ? 0 : 1);
+          ++launches;
+        }
         first = false;
       }
     }
   }
+  // thP (+)= Theta+ G_t, thN (+)= Theta- G_t from the plane sets of an FZ_BF16X3 constraint matrix and the operand form of G_t
+  // that the iteration's products use (in the centred form G = 1 c^T + D the rank-1 parts rowsum(Theta+-) c^T are added here)
+  void theta_tc(TypeRec& t, RelRec& r, bool first, cudaStream_t st);
 
   void build_job_tables() {
     std::vector<PinvJob> pj;
@@ -2074,17 +2191,23 @@ class Engine : public EngineBase {
 };
 
 template <>
-void Engine<float>::umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g_row0, float* C, int64_t ldc, int M, int K, int k,
-                         cudaStream_t st) {
+void Engine<float>::umma(const PlaneSet& ps, bool trans, const CUtensorMap& tg, int64_t g_row0, float* C, int64_t ldc, int M, int K, int k,
+                         bool accumulate, cudaStream_t st) {
+  if (M <= 0) return;
+  if (ps.n == 0 || K <= 0) {      // an all-zero matrix (e.g. the empty sign part of a constraint): the product is zero
+    if (!accumulate) CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st));
+    return;
+  }
   SkinnyParams p;
-  p.C = C;
   p.ldc = ldc;
   p.M = M;
   p.K = K;
-  p.k = k;
   p.kp = kKp;
   p.terms = gs_terms_;
   p.g_row0 = (int)g_row0;
+  const int kp_g = ((k + kKp - 1) / kKp) * kKp;      // padded rank of the operand: its terms are kp_g columns apart
+  const int col_blocks = kp_g / kKp;
+  p.g_term_stride = kp_g;
   // split the reduction so that the grid covers the machine a few times over
   const int row_blocks = (M + kSkBM - 1) / kSkBM;
   int ksplit = 1;
@@ -2094,19 +2217,26 @@ void Engine<float>::umma(RelRec& r, bool trans, const CUtensorMap& tg, int64_t g
   int kps = ((K + ksplit - 1) / ksplit + 63) / 64 * 64;
   ksplit = (K + kps - 1) / kps;
   p.k_per_split = kps;
-  p.atomic = ksplit > 1 ? 1 : 0;
-  if (p.atomic) CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st));
-  const CUtensorMap& tx = trans ? r.tmXT : r.tmX;
+  p.atomic = (ksplit > 1 || ps.n > 1 || accumulate) ? 1 : 0;
+  if (p.atomic && !accumulate) CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st));
   const int N = gs_terms_ * kKp;
   prof_begin(st);
-  if (N == 64) { if (trans) umma_launch<64, true>(tx, tg, p, ksplit, st); else umma_launch<64, false>(tx, tg, p, ksplit, st); }
-  else if (N == 128) { if (trans) umma_launch<128, true>(tx, tg, p, ksplit, st); else umma_launch<128, false>(tx, tg, p, ksplit, st); }
-  else { if (trans) umma_launch<192, true>(tx, tg, p, ksplit, st); else umma_launch<192, false>(tx, tg, p, ksplit, st); }
-  prof_end(st, 2.0 * (double)M * (double)K);
+  for (int q = 0; q < ps.n; ++q) {
+    const CUtensorMap& tx = trans ? ps.tmXT[q] : ps.tmX[q];
+    for (int cb = 0; cb < col_blocks; ++cb) {
+      p.C = C + cb * kKp;
+      p.k = std::min(kKp, k - cb * kKp);
+      p.g_col0 = cb * kKp;
+      if (N == 64) { if (trans) umma_launch<64, true>(tx, tg, p, ksplit, st); else umma_launch<64, false>(tx, tg, p, ksplit, st); }
+      else if (N == 128) { if (trans) umma_launch<128, true>(tx, tg, p, ksplit, st); else umma_launch<128, false>(tx, tg, p, ksplit, st); }
+      else { if (trans) umma_launch<192, true>(tx, tg, p, ksplit, st); else umma_launch<192, false>(tx, tg, p, ksplit, st); }
+    }
+  }
+  prof_end(st, 2.0 * (double)M * (double)K * ps.n * col_blocks);
 }
 template <>
 bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
-  if (!fused_ || r.storage != FZ_BF16 || r.rows_loc <= 0) return false;
+  if (!fused_ || !r.tc || r.rows_loc <= 0) return false;
   TypeRec& Ti = *types_[r.ti];
   TypeRec& Tj = *types_[r.tj];
   FusedParams p;
@@ -2150,7 +2280,8 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   splits = std::max(1, std::min(splits, tiles));
   p.tiles_per_split = (tiles + splits - 1) / splits;
   splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.a_atomic = (splits > 1 || single_now_) ? 1 : 0;     // the single-term kernel always reduces into A
+  const int n_planes = r.pl.n;                           // FZ_BF16X3: one pass per bf16 plane, all reducing into the same A and B
+  p.a_atomic = (splits > 1 || single_now_ || n_planes > 1) ? 1 : 0;     // the single-term kernel always reduces into A
   if (centred_ && comm_ == nullptr) {    // B starts from the rank-1 part colsum(R) c_i^T of the centred form
     rank1_init<<<nblk(Tj.n_pad * Ti.k, 256), 256, 0, st>>>(r.B.template as<float>(), Ti.k, Tj.n_pad, r.cols, Ti.k, r.colsum.template as<float>(),
                                                            Ti.centre.template as<float>());
@@ -2161,6 +2292,9 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
   if (p.a_atomic) CUDA_OK(cudaMemsetAsync(r.A.p, 0, (size_t)r.rows_loc * Tj.k * sizeof(float), st));
   dim3 grid(pairs, splits);
   prof_begin(st);
+  for (int plane = 0; plane < n_planes; ++plane) {
+  const CUtensorMap& tmx = r.pl.tmX[plane];
+  if (plane > 0) p.rowsum = nullptr;      // the rank-1 part rowsum(R) c_j^T (row sums of the WHOLE relation) enters once
   if (single_now_) {
     Fused1Params q;
     q.A = p.A; q.B = p.B; q.lda = p.lda; q.ldb = p.ldb; q.rowsum = p.rowsum; q.cj = p.cj;
@@ -2178,8 +2312,8 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
       q.work_counter = sched_ctr_.template as<int>();
       CUDA_OK(cudaMemsetAsync(q.work_counter, 0, sizeof(int), st));
     }
-    umma_fused1_kernel<<<ctas, kF1Threads, kF1SmemBytes, st>>>(r.tmX, Tj.tmG128, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX,
-                                                               r.has_tmA ? r.tmA : r.tmX, q);
+    umma_fused1_kernel<<<ctas, kF1Threads, kF1SmemBytes, st>>>(tmx, Tj.tmG128, Ti.tmG128, r.has_tmB ? r.tmB : tmx,
+                                                               r.has_tmA ? r.tmA : tmx, q);
   } else if (fused_ver_ == 4 && r.v4_ok && !centred_) {
     FusedTParams q;
     q.A = p.A; q.B = p.B; q.lda = p.lda; q.ldb = p.ldb;
@@ -2191,10 +2325,11 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
     q.variant = 0;
     umma_fused_t_kernel<<<grid, kFtThreads, kFtSmemBytes, st>>>(r.tmX256, Tj.tmGT, r.has_tmB16 ? r.tmB16 : r.tmX256, q);
   } else {
-    umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(r.tmX, Tj.tmG, Ti.tmG128, r.has_tmB ? r.tmB : r.tmX, r.has_tmB ? r.tmB : r.tmX, p);
+    umma_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(tmx, Tj.tmG, Ti.tmG128, r.has_tmB ? r.tmB : tmx, r.has_tmB ? r.tmB : tmx, p);
   }
   ++launches;
-  prof_end(st, 2.0 * (double)r.rows_loc * (double)r.cols, /*passes=*/1);
+  }
+  prof_end(st, 2.0 * (double)r.rows_loc * (double)r.cols * n_planes, /*passes=*/1);
   return true;
 }
 template <>
@@ -2352,13 +2487,31 @@ void Engine<float>::rank1_add_local(RelRec& r, cudaStream_t st) {
 template <>
 void Engine<double>::rank1_add_local(RelRec&, cudaStream_t) {}
 template <>
+void Engine<float>::theta_tc(TypeRec& t, RelRec& r, bool first, cudaStream_t st) {
+  float* outs[2] = {t.thP.template as<float>(), t.thN.template as<float>()};      // den <- Theta+ G, num <- Theta- G
+  const PlaneSet* sets[2] = {&r.pl, &r.pl_neg};
+  for (int side = 0; side < 2; ++side) {
+    umma(*sets[side], false, t.tmG, 0, outs[side], t.k, (int)r.rows_loc, (int)r.cols, t.k, /*accumulate=*/!first, st);
+    if (t.gs_centred && sets[side]->n > 0) {
+      if (sets[side]->rowsum.p == nullptr) FZ_THROW(FZ_ERR_INVALID, "centred operand form without the constraint's row sums");
+      rank1_add<<<nblk(r.rows_loc * t.k, 256), 256, 0, st>>>(outs[side], t.k, r.rows_loc, t.k, sets[side]->rowsum.template as<float>(),
+                                                             t.centre.template as<float>());
+      ++launches;
+    }
+  }
+}
+template <>
+void Engine<double>::theta_tc(TypeRec&, RelRec&, bool, cudaStream_t) {
+  FZ_THROW(FZ_ERR_UNSUPPORTED, "tensor-core path needs the fp32 engine");
+}
+template <>
 void Engine<float>::gate_measure(RelRec& r, int rel, cudaStream_t st) {
-  if (r.theta || r.storage != FZ_BF16 || r.rows_loc <= 0) return;
+  if (r.theta || !r.tc || r.rows_loc <= 0) return;
   TypeRec& Ti = *types_[r.ti];
   TypeRec& Tj = *types_[r.tj];
   int slot = 0;
   for (int q = 0; q < rel; ++q)
-    if (!rels_[q]->theta && rels_[q]->storage == FZ_BF16) slot += 4;
+    if (!rels_[q]->theta && rels_[q]->tc) slot += 4;
   float* probe_a = gate_probe_.template as<float>();
   float* probe_b = probe_a + 128 * 64;
   CUDA_OK(cudaMemsetAsync(probe_a, 0, (size_t)2 * 128 * 64 * sizeof(float), st));
@@ -2394,7 +2547,7 @@ template <>
 void Engine<double>::gate_measure(RelRec&, int, cudaStream_t) {}
 
 template <>
-void Engine<double>::umma(RelRec&, bool, const CUtensorMap&, int64_t, double*, int64_t, int, int, int, cudaStream_t) {
+void Engine<double>::umma(const PlaneSet&, bool, const CUtensorMap&, int64_t, double*, int64_t, int, int, int, bool, cudaStream_t) {
   FZ_THROW(FZ_ERR_UNSUPPORTED, "tensor-core path needs the fp32 engine");
 }
 

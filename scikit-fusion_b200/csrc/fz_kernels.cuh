@@ -876,6 +876,73 @@ __global__ void convert_2d_from_bf16(const __nv_bfloat16* __restrict__ src, long
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32 relation -> bf16 planes (storage FZ_BF16X3): X = P0 + P1 + P2 EXACTLY, P_t = bf16 rounding of the running residual
+// (three round-to-nearest 8-bit terms cover the 24-bit significand).  The planes feed the same tcgen05 kernels as a
+// bf16-stored relation, one pass per non-zero plane, accumulating into the same outputs, so an fp32 relation reaches the
+// tensor cores without losing a bit of R.  `part`: 0 the value itself, +1 max(x, 0), -1 max(-x, 0) (the two halves of a
+// constraint matrix, _dfmf.py:203-208).  (Own design: no counterpart in the reference.)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float plane_part(float v, int part) {
+  if (part > 0) return v > 0.f ? v : 0.f;
+  if (part < 0) return v < 0.f ? -v : 0.f;
+  return v;
+}
+// need[t] = 1 when plane t of the split holds a non-zero somewhere (integers, ratings, 0/1 data fit plane 0 alone)
+__global__ void planes_needed(const float* __restrict__ X, long long ld, long long rows, long long cols, int part,
+                              unsigned int* __restrict__ need) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  float v = plane_part(X[(idx / cols) * ld + (idx % cols)], part);
+  if (v != v || fabsf(v) > 3.3e38f) { need[3] = 1u; return; }        // non-finite entries cannot be split: refused by the caller
+  if (v != 0.f) need[0] = 1u;
+  v -= __bfloat162float(__float2bfloat16_rn(v));
+  if (v != 0.f) need[1] = 1u;
+  v -= __bfloat162float(__float2bfloat16_rn(v));
+  if (v != 0.f) need[2] = 1u;
+}
+// P[t][r][c] = term t (t < n_planes); plane t starts at P + t * plane_stride, rows pitched to ldp (pad columns stay zero)
+__global__ void split_planes(const float* __restrict__ X, long long ld, __nv_bfloat16* __restrict__ P, long long ldp,
+                             long long plane_stride, int n_planes, long long rows, long long cols, int part) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols, c = idx % cols;
+  float v = plane_part(X[r * ld + c], part);
+  __nv_bfloat16* out = P + r * ldp + c;
+  for (int t = 0; t < n_planes; ++t) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[(long long)t * plane_stride] = h;
+    v -= __bfloat162float(h);
+  }
+}
+// the same for the masked entries only (dfmc re-imputes them every iteration; the known entries never change)
+__global__ void split_planes_masked(const float* __restrict__ X, long long ld, const uint8_t* __restrict__ mask, long long mld,
+                                    __nv_bfloat16* __restrict__ P, long long ldp, long long plane_stride, int n_planes,
+                                    long long rows, long long cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols, c = idx % cols;
+  if (!mask[r * mld + c]) return;
+  float v = X[r * ld + c];
+  __nv_bfloat16* out = P + r * ldp + c;
+  for (int t = 0; t < n_planes; ++t) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[(long long)t * plane_stride] = h;
+    v -= __bfloat162float(h);
+  }
+}
+// out[r] = sum over the columns of one sign part of X (fp64 accumulation): the rank-1 part of Theta+- G in the centred form
+__global__ void row_sums_part(const float* __restrict__ X, long long ld, long long rows, long long cols, int part,
+                              float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (long long c = lane; c < cols; c += 32) s += (double)plane_part(X[r * ld + c], part);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = (float)s;
+}
+
+// ------------------------------------------------------------------------------------------------
 // dfmc: R[mask] = 0 before the first iteration (_dfmc.py:287-292) and
 //       R[mask] = (G_i S G_j^T)[mask] after every S-update (_dfmc.py:319-325);  T1 = G_i S is given.
 // ------------------------------------------------------------------------------------------------

@@ -33,7 +33,9 @@ struct SkinnyParams {
   int k_per_split;     // reduction elements handled per blockIdx.y (multiple of 64)
   int atomic;          // 1: red.add into C (split-K), 0: plain store
   int g_row0;          // first row of Gs that pairs with reduction index 0 (row-sharded factors)
-  int g_col0 = 0;      // first column of Gs read as term 0 (64 = the residual term of a two-term operand: error probes)
+  int g_col0 = 0;      // first column of Gs read as term 0 (64 = the residual term of a two-term operand: error probes;
+                       // c * 64 = the c-th 64-column block of a factor of rank > 64)
+  int g_term_stride = 64;   // columns of Gs between consecutive terms of the operand (the padded rank of the factor)
 };
 
 constexpr int kSkBM = 128;   // rows of C per CTA == UMMA M
@@ -107,7 +109,7 @@ umma_skinny_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
 #pragma unroll
         for (int ch = 0; ch < N / 64; ++ch)
-          ptx::tma_load_2d(gs + ch * 8192, &tmG, &full_bar[s], p.g_col0 + ch * 64, p.g_row0 + k0, ptx::kEvictLast);
+          ptx::tma_load_2d(gs + ch * 8192, &tmG, &full_bar[s], p.g_col0 + ch * p.g_term_stride, p.g_row0 + k0, ptx::kEvictLast);
       }
     }
   } else if (warp == 1) {

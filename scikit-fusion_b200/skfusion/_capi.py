@@ -14,7 +14,7 @@ PKG_ROOT = os.path.dirname(_HERE)                      # scikit-fusion_b200/
 LIB_PATH = os.path.join(PKG_ROOT, "libfz_fusion.so")
 CSRC = os.path.join(PKG_ROOT, "csrc")
 
-FZ_F64, FZ_F32, FZ_BF16, FZ_U8 = 0, 1, 2, 3
+FZ_F64, FZ_F32, FZ_BF16, FZ_U8, FZ_BF16X3 = 0, 1, 2, 3, 4
 FZ_HOST, FZ_DEVICE = 0, 1
 FZ_DFMF, FZ_DFMC = 0, 1
 FZ_TERMS_AUTO, FZ_TERMS_CENTRED1 = 0, -1
@@ -139,7 +139,7 @@ def lib():
 _NP2FZ = {np.dtype(np.float64): FZ_F64, np.dtype(np.float32): FZ_F32, np.dtype(np.uint8): FZ_U8,
           np.dtype(np.bool_): FZ_U8}
 _DTYPE_NAMES = {"float64": FZ_F64, "float32": FZ_F32, "bfloat16": FZ_BF16, "f64": FZ_F64, "f32": FZ_F32,
-                "bf16": FZ_BF16}
+                "bf16": FZ_BF16, "bfloat16x3": FZ_BF16X3, "bf16x3": FZ_BF16X3}
 
 
 def dtype_code(name):
@@ -148,7 +148,7 @@ def dtype_code(name):
     try:
         return _DTYPE_NAMES[str(name).replace("torch.", "")]
     except KeyError:
-        raise ValueError("unknown dtype %r (float64 | float32 | bfloat16)" % (name,))
+        raise ValueError("unknown dtype %r (float64 | float32 | bfloat16 | bfloat16x3 [storage only])" % (name,))
 
 
 def comm_unique_id():
@@ -413,7 +413,8 @@ class Engine(object):
 
     def add_relation_borrowed(self, ti, tj, ptr, ld, code):
         """A relation that lives in another handle's device memory (same device): borrowed, never copied."""
-        rid = self._ck(self._L.fz_add_relation(self._h, ti, tj, ctypes.c_void_p(ptr), int(ld), int(code), FZ_DEVICE, int(code), 1, None, 0,
+        src = FZ_F32 if int(code) == FZ_BF16X3 else int(code)      # bf16x3: the fp32 master is borrowed, the planes are this handle's
+        rid = self._ck(self._L.fz_add_relation(self._h, ti, tj, ctypes.c_void_p(ptr), int(ld), src, FZ_DEVICE, int(code), 1, None, 0,
                                                FZ_HOST))
         self.rel_types.append((ti, tj))
         return rid

@@ -8,8 +8,13 @@ Defaults can be changed process-wide (``engine_options.update(dtype='float64')``
                fast path (G <= 1e-4..1e-3, S <= 1e-3..5e-3 depending on conditioning).  'auto' takes float64 while
                the graph is small (<= AUTO_FP64_MAX_ENTRIES relation entries: every dataset the reference ships),
                where B200's fp64 rate makes exactness free, and float32 beyond -- or whenever storage is bfloat16.
-  storage      device dtype of relation matrices: None (= dtype), or 'bfloat16' to take the
-               tcgen05 tensor-core path (rank <= 64, fp32 engine)
+  storage      device form of the relation matrices: None (= dtype: exact CUDA-core products), 'bfloat16' (the relation
+               rounded to bf16, streamed once per iteration through the fused tcgen05 kernels: the fastest path, exact
+               for 0/1 data, small integers, ratings ...), or 'bfloat16x3' (float32 engine): the float32 relation kept
+               exactly as up to three bf16 planes, one tensor-core pass per non-zero plane -- also for masked relations
+               (Dfmc), constraint matrices and ranks above 64.  With dtype='auto' and no storage given, graphs beyond
+               AUTO_FP64_MAX_ENTRIES entries on one GPU take 'bfloat16x3' (no bit of R is lost; the factor operand
+               carries 16 bits, as on the bfloat16 path).
   split_terms  operand form of the factors on the tensor-core path: 1..3 bf16 terms of the factor itself, or 'auto' --
                the mean-centred form with the single-term / two-term kernel chosen per iteration from a measured error
                estimate (include/fz_fusion.h: FZ_TERMS_AUTO) -- or 'centred1' (always the single-term kernel)
@@ -56,4 +61,7 @@ def resolve(n_entries=None, **overrides):
     if opts["dtype"] == "auto":
         small = n_entries is not None and n_entries <= AUTO_FP64_MAX_ENTRIES
         opts["dtype"] = "float64" if (small and not opts.get("storage")) else "float32"
+        if (not opts.get("storage") and n_entries is not None and not small and int(opts.get("n_gpus") or 1) == 1
+                and os.environ.get("SKFUSION_B200_AUTO_X3", "1") != "0"):
+            opts["storage"] = "bfloat16x3"      # large float32 graphs: exact bf16 planes on the tensor cores
     return opts

@@ -98,9 +98,11 @@ class _Problem(object):
                                                     storage=storage, borrow=self._can_borrow(mat, storage, mask),
                                                     mask=mask))
             self.rel_ids[key] = ids
+        # constraint matrices stay exact: in the compute dtype, or (storage bfloat16x3) as exact bf16 planes on the tensor cores
+        th_storage = storage if (storage and _capi.dtype_code(storage) == _capi.FZ_BF16X3) else None
         for key, mats in Theta.items():
             for mat in mats:
-                self.engine.add_relation(self.type_id[key[0]], self.type_id[key[1]], mat, storage=None)
+                self.engine.add_relation(self.type_id[key[0]], self.type_id[key[1]], mat, storage=th_storage)
 
     def _can_borrow(self, mat, storage, mask):
         if mask is not None or not _capi._is_torch_cuda(mat):
@@ -457,7 +459,8 @@ def transform(R_ij, Theta_i, target_obj_type, obj_type2rank, G, S, max_iter=10, 
                 rel_of.append((rid, (ti, tj), l))
         for key, mats in Theta_i.items():
             for mat in mats:
-                prob.engine.add_relation(prob.type_id[id(tgt)], prob.type_id[id(tgt)], mat, storage=None)
+                prob.engine.add_relation(prob.type_id[id(tgt)], prob.type_id[id(tgt)], mat,
+                                         storage=storage if (storage and _capi.dtype_code(storage) == _capi.FZ_BF16X3) else None)
         for t in involved:
             if not (on_device and t is tgt):
                 prob.engine.set_factor(prob.type_id[id(t)], G_i if t is tgt else G[t, t])

@@ -13,12 +13,16 @@ from helpers import rel_fro
 pytestmark = pytest.mark.gpu
 
 
-def _run(world, storage, dtype, n, iters, terms=2):
+def _run(world, storage, dtype, n, iters, terms=2, graph=None):
     import torch
     from skfusion import _capi
     from skfusion.fusion import distributed as fzd
-    types, ranks, R = oracle.hashed_graph(n, n_types=3, rank=64 if storage == "bfloat16" else 24, storage=storage or "float64")
-    sizes = {t: n for t in types}
+    if graph is not None:
+        types, ranks, R = graph
+        sizes = oracle.count_objects(R)
+    else:
+        types, ranks, R = oracle.hashed_graph(n, n_types=3, rank=64 if storage == "bfloat16" else 24, storage=storage or "float64")
+        sizes = {t: n for t in types}
     G0 = oracle.initialize(types, sizes, ranks, {}, "random", np.random.RandomState(0))
     shards = []
     for rank in range(world):
