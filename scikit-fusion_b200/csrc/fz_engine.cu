@@ -1781,6 +1781,7 @@ class Engine : public EngineBase {
     umma_attr<64, false>(); umma_attr<64, true>();
     umma_attr<128, false>(); umma_attr<128, true>();
     umma_attr<192, false>(); umma_attr<192, true>();
+    umma_attr<256, false>(); umma_attr<256, true>();
     cudaFuncSetAttribute(umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes);
     cudaFuncSetAttribute(umma_fused1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF1SmemBytes);
     cudaFuncSetAttribute(umma_fused_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes);
@@ -2206,7 +2207,9 @@ void Engine<float>::umma(const PlaneSet& ps, bool trans, const CUtensorMap& tg, 
   p.terms = gs_terms_;
   p.g_row0 = (int)g_row0;
   const int kp_g = ((k + kKp - 1) / kKp) * kKp;      // padded rank of the operand: its terms are kp_g columns apart
-  const int col_blocks = kp_g / kKp;
+  // factors of rank > 64 go through in column blocks: 128 columns per launch (accumulator N = 256) with two terms, else 64
+  const int block_w = (k > kKp && gs_terms_ == 2) ? 2 * kKp : kKp;
+  const int col_blocks = (kp_g + block_w - 1) / block_w;
   p.g_term_stride = kp_g;
   // split the reduction so that the grid covers the machine a few times over
   const int row_blocks = (M + kSkBM - 1) / kSkBM;
@@ -2219,17 +2222,21 @@ void Engine<float>::umma(const PlaneSet& ps, bool trans, const CUtensorMap& tg, 
   p.k_per_split = kps;
   p.atomic = (ksplit > 1 || ps.n > 1 || accumulate) ? 1 : 0;
   if (p.atomic && !accumulate) CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st));
-  const int N = gs_terms_ * kKp;
   prof_begin(st);
   for (int q = 0; q < ps.n; ++q) {
     const CUtensorMap& tx = trans ? ps.tmXT[q] : ps.tmX[q];
     for (int cb = 0; cb < col_blocks; ++cb) {
-      p.C = C + cb * kKp;
-      p.k = std::min(kKp, k - cb * kKp);
-      p.g_col0 = cb * kKp;
+      const int w = std::min(block_w, kp_g - cb * block_w);      // 64 or 128 operand columns in this launch
+      p.C = C + cb * block_w;
+      p.k = std::min(w, k - cb * block_w);
+      p.kp = w;
+      p.chunks_per_term = w / kKp;
+      p.g_col0 = cb * block_w;
+      const int N = gs_terms_ * w;
       if (N == 64) { if (trans) umma_launch<64, true>(tx, tg, p, ksplit, st); else umma_launch<64, false>(tx, tg, p, ksplit, st); }
       else if (N == 128) { if (trans) umma_launch<128, true>(tx, tg, p, ksplit, st); else umma_launch<128, false>(tx, tg, p, ksplit, st); }
-      else { if (trans) umma_launch<192, true>(tx, tg, p, ksplit, st); else umma_launch<192, false>(tx, tg, p, ksplit, st); }
+      else if (N == 192) { if (trans) umma_launch<192, true>(tx, tg, p, ksplit, st); else umma_launch<192, false>(tx, tg, p, ksplit, st); }
+      else { if (trans) umma_launch<256, true>(tx, tg, p, ksplit, st); else umma_launch<256, false>(tx, tg, p, ksplit, st); }
     }
   }
   prof_end(st, 2.0 * (double)M * (double)K * ps.n * col_blocks);

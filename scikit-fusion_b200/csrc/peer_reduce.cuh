@@ -122,36 +122,4 @@ pull_reduce(PeerPtrs src, PeerFlags f, float* __restrict__ Bloc, long long row0,
   }
 }
 
-// ---- all-gather of an updated factor over peer memory: every rank PUSHES its rows into the peers' copies ------------------
-struct PeerRows {
-  float* G[kMaxPeers];                // every rank's copy of the factor buffer being written this iteration, as mapped here
-};
-// dst_p[row0 + r][:] = src[row0 + r][:] for every peer p != rank (float4 copies; rows x k floats, k % 4 == 0); the last block to
-// finish tells every rank (itself included) that this rank's rows of type `t` for `epoch` are in place.
-__global__ void __launch_bounds__(256)
-push_rows(PeerRows dst, const float* __restrict__ mine, long long row0, long long rows, int k, unsigned long long* const* g_arrive_ptrs,
-          unsigned int* __restrict__ done_ctr, int world, int rank, int n_types, int t, unsigned long long epoch) {
-  const long long n_vec = rows * (k >> 2);
-  const float4* src = reinterpret_cast<const float4*>(mine + row0 * k);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = src[i];
-    for (int p = 0; p < world; ++p)
-      if (p != rank) reinterpret_cast<float4*>(dst.G[p] + row0 * k)[i] = v;
-  }
-  __shared__ unsigned int last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    last = (atomicAdd(done_ctr, 1u) == gridDim.x - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (last) {
-    if (threadIdx.x == 0) *done_ctr = 0;
-    if (threadIdx.x < world) {
-      __threadfence_system();
-      st_release_sys(g_arrive_ptrs[threadIdx.x] + (size_t)rank * n_types + t, epoch);
-    }
-  }
-}
-
 }  // namespace fz

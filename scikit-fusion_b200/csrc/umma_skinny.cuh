@@ -36,6 +36,7 @@ struct SkinnyParams {
   int g_col0 = 0;      // first column of Gs read as term 0 (64 = the residual term of a two-term operand: error probes;
                        // c * 64 = the c-th 64-column block of a factor of rank > 64)
   int g_term_stride = 64;   // columns of Gs between consecutive terms of the operand (the padded rank of the factor)
+  int chunks_per_term = 1;  // 64-column chunks of Gs per term in this launch (kp / 64): 2 = a 128-column block of a wide factor
 };
 
 constexpr int kSkBM = 128;   // rows of C per CTA == UMMA M
@@ -109,7 +110,9 @@ umma_skinny_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
 #pragma unroll
         for (int ch = 0; ch < N / 64; ++ch)
-          ptx::tma_load_2d(gs + ch * 8192, &tmG, &full_bar[s], p.g_col0 + ch * p.g_term_stride, p.g_row0 + k0, ptx::kEvictLast);
+          ptx::tma_load_2d(gs + ch * 8192, &tmG, &full_bar[s],
+                           p.g_col0 + (ch / p.chunks_per_term) * p.g_term_stride + (ch % p.chunks_per_term) * 64, p.g_row0 + k0,
+                           ptx::kEvictLast);
       }
     }
   } else if (warp == 1) {

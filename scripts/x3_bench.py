@@ -1,7 +1,7 @@
 """float32 relations at scale: exact CUDA-core path vs bf16 planes on the tensor cores (storage='bfloat16x3') vs bf16 storage,
 plus ranks above 64.  One JSON line per configuration (it/s with the relations resident in HBM, CUDA events around the
 iterations; relFro of the factors against the float32 CUDA-core run of the same seeds).  Verdict row J2.
-    python scripts/x3_bench.py [n] [iters]
+    python scripts/x3_bench.py [n] [iters] [comma-separated workload labels]
 """
 import json
 import os
@@ -19,6 +19,7 @@ def main():
     from skfusion import _capi
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    only = set(sys.argv[3].split(",")) if len(sys.argv) > 3 else None
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)
@@ -27,9 +28,11 @@ def main():
     R32 = {p: torch.rand((n, n), generator=gen, device=dev, dtype=torch.float32) for p in pairs}
     ratings = {p: torch.randint(0, 6, (n, n), generator=gen, device=dev).to(torch.float32) for p in pairs}
     theta = torch.where(torch.rand((n, n), generator=gen, device=dev) < 0.001, -0.005, 0.0).to(torch.float32)
+    unknown = (torch.rand((n, n), generator=gen, device=dev) < 0.3).to(torch.uint8)      # dfmc: 30 % of relation (0, 1) unknown
     results = {}
 
-    def run(label, data, storage, rank, with_theta=False, terms="auto"):
+    def run(label, data, storage, rank, with_theta=False, terms="auto", algo=None):
+        algo = _capi.FZ_DFMF if algo is None else algo
         eng = _capi.Engine(device=0, compute="float32")
         try:
             eng.set_split_terms(terms)
@@ -38,19 +41,20 @@ def main():
                 mat = data[i, j]
                 if storage == "bfloat16":
                     mat = mat.to(torch.bfloat16)
-                eng.add_relation(tids[i], tids[j], mat, storage=storage, borrow=True)
+                masked = algo == _capi.FZ_DFMC and (i, j) == pairs[0]
+                eng.add_relation(tids[i], tids[j], mat, storage=storage, borrow=not masked, mask=unknown if masked else None)
             if with_theta:
                 eng.add_relation(tids[0], tids[0], theta, storage=storage if storage == "bfloat16x3" else None, borrow=True)
             rs = np.random.RandomState(0)
             for t in tids:
                 eng.set_factor(t, rs.rand(n, rank).astype(np.float32))
             eng.finalize()
-            eng.iterate(_capi.FZ_DFMF, 3)
+            eng.iterate(algo, 3)
             torch.cuda.synchronize()
             l0 = eng.launches
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            eng.iterate(_capi.FZ_DFMF, iters, torch.cuda.current_stream().cuda_stream)
+            eng.iterate(algo, iters, torch.cuda.current_stream().cuda_stream)
             b.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / iters
@@ -69,7 +73,7 @@ def main():
         return float(np.linalg.norm(a - b) / np.linalg.norm(a))
 
     lines = []
-    for label, data, storage, rank, th in [
+    for label, data, storage, rank, th, algo in [(c + (None,) if len(c) == 5 else c) for c in [
             ("f32 cuda-core", R32, None, 64, False),
             ("f32 planes", R32, "bfloat16x3", 64, False),
             ("f32 rounded to bf16", R32, "bfloat16", 64, False),
@@ -78,12 +82,16 @@ def main():
             ("ratings cuda-core", ratings, None, 64, False),
             ("ratings planes", ratings, "bfloat16x3", 64, False),
             ("rank128 cuda-core", R32, None, 128, False),
-            ("rank128 planes", R32, "bfloat16x3", 128, False)]:
+            ("rank128 planes", R32, "bfloat16x3", 128, False),
+            ("completion cuda-core", R32, None, 64, False, _capi.FZ_DFMC),
+            ("completion planes", R32, "bfloat16x3", 64, False, _capi.FZ_DFMC)]]:
+        if only is not None and label not in only:
+            continue
         t0 = time.time()
-        line = run(label, data, storage, rank, th)
+        line = run(label, data, storage, rank, th, algo=algo)
         base = {"f32 planes": "f32 cuda-core", "f32 rounded to bf16": "f32 cuda-core", "f32 planes + constraint": "f32 cuda-core + constraint",
-                "ratings planes": "ratings cuda-core", "rank128 planes": "rank128 cuda-core"}.get(label)
-        if base:
+                "ratings planes": "ratings cuda-core", "rank128 planes": "rank128 cuda-core", "completion planes": "completion cuda-core"}.get(label)
+        if base and base in results:
             line["relFro_G_vs_cuda_core"] = max(rel(a, b) for a, b in zip(results[base], results[label]))
         line["wall_s"] = round(time.time() - t0, 1)
         print(json.dumps(line), flush=True)

@@ -165,6 +165,51 @@ def test_sharded_handles_with_exact_planes_match_the_oracle(terms):
     _check(Go, So, G, S, types, 1e-4, 1e-3)
 
 
+@pytest.mark.parametrize("init", ["random_c", "random_vcol"])
+def test_device_side_initialisation_streams_the_planes(init):
+    """random_c / random_vcol with the column means computed on the GPU (device_init=True): the sampled means and the
+    column norms come from the planes / the float32 master and equal the host initialisation."""
+    from skfusion.fusion import solver
+    types, ranks, R = _graph((520, 392, 300), (40, 64, 24), 17)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Go, So = oracle.dfmf(R, {}, types, ranks, max_iter=8, init_type=init, random_state=np.random.RandomState(3))
+        G, S = solver.dfmf(R, {}, types, ranks, max_iter=8, init_type=init, random_state=np.random.RandomState(3),
+                           dtype="float32", storage="bfloat16x3", device_init=True)
+    _check(Go, So, G, S, types, 1e-3, 5e-3)
+
+
+def test_estimators_take_the_storage_keyword():
+    """Dfmf / Dfmc / DfmfTransform(storage='bfloat16x3') through the reference-facing API, constraint included."""
+    import cases
+    from skfusion.fusion import Dfmc, Dfmf, DfmfTransform, FusionGraph, ObjectType, Relation
+    rs = np.random.RandomState(0)
+    t1, t2, t3 = ObjectType("a", 24), ObjectType("b", 32), ObjectType("c", 16)
+    R12 = rs.rand(392, 520).astype(np.float32).astype(np.float64)
+    R13 = rs.rand(392, 264).astype(np.float32).astype(np.float64)
+    th = cases._sparse_sym_constraint(rs, 392, density=0.02, scale=0.1)
+    rels = [Relation(R12, t1, t2), Relation(R13, t1, t3), Relation(th, t1, t1)]
+    kw = dict(max_iter=10, init_type="random")
+    exact = Dfmf(random_state=np.random.RandomState(1), dtype="float64", **kw).fuse(FusionGraph(rels))
+    fast = Dfmf(random_state=np.random.RandomState(1), dtype="float32", storage="bfloat16x3", **kw).fuse(FusionGraph(rels))
+    for t in (t1, t2, t3):
+        assert rel_fro(exact.factor(t), fast.factor(t)) < 1e-4
+    assert rel_fro(exact.complete(rels[0]), fast.complete(rels[0])) < 1e-4
+    # completion: 30 % of R12 unknown
+    masked = np.ma.masked_array(R12, mask=rs.rand(392, 520) < 0.3)
+    rels_c = [Relation(masked, t1, t2), Relation(R13, t1, t3)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exact_c = Dfmc(random_state=np.random.RandomState(2), dtype="float64", **kw).fuse(FusionGraph(rels_c))
+        fast_c = Dfmc(random_state=np.random.RandomState(2), dtype="float32", storage="bfloat16x3", **kw).fuse(FusionGraph(rels_c))
+    assert rel_fro(exact_c.complete(rels_c[0]), fast_c.complete(rels_c[0])) < 2e-4
+    # projection of new rows of type a
+    new_graph = FusionGraph([Relation(R12[:136].copy(), t1, t2), Relation(R13[:136].copy(), t1, t3)])
+    te = DfmfTransform(random_state=np.random.RandomState(3), dtype="float64", max_iter=10).transform(t1, new_graph, exact)
+    tf = DfmfTransform(random_state=np.random.RandomState(3), dtype="float32", storage="bfloat16x3", max_iter=10).transform(t1, new_graph, exact)
+    assert rel_fro(te.factor(t1), tf.factor(t1)) < 1e-4
+
+
 def test_non_finite_entries_are_refused():
     from skfusion import _capi
     eng = _capi.Engine(device=0, compute="float32")

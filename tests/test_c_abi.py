@@ -22,6 +22,32 @@ def test_header_declares_the_bound_symbols():
     assert sorted(_capi.SYMBOLS) == _declared()
 
 
+def test_header_enums_match_the_binding():
+    """dtype / memory / algorithm codes of include/fz_fusion.h are the ones skfusion/_capi.py passes."""
+    from skfusion import _capi
+    text = open(HEADER).read()
+    found = {name: int(val) for name, val in re.findall(r"\b(FZ_[A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
+    for name in ("FZ_F64", "FZ_F32", "FZ_BF16", "FZ_U8", "FZ_BF16X3", "FZ_HOST", "FZ_DEVICE", "FZ_DFMF", "FZ_DFMC",
+                 "FZ_TERMS_AUTO", "FZ_TERMS_CENTRED1"):
+        assert found[name] == getattr(_capi, name), name
+    assert _capi.dtype_code("bfloat16x3") == _capi.FZ_BF16X3 == found["FZ_BF16X3"]
+
+
+def test_storage_of_large_float32_graphs_defaults_to_exact_planes():
+    """options.resolve: dtype='auto' keeps float64 for small graphs and takes the float32 engine with the relations as exact bf16
+    planes (tensor cores, no bit of R lost) beyond AUTO_FP64_MAX_ENTRIES on one GPU; an explicit choice is never overridden."""
+    from skfusion.fusion import options
+    big = options.AUTO_FP64_MAX_ENTRIES + 1
+    assert options.resolve(n_entries=1000)["dtype"] == "float64" and not options.resolve(n_entries=1000).get("storage")
+    got = options.resolve(n_entries=big)
+    assert got["dtype"] == "float32" and got["storage"] == "bfloat16x3"
+    assert options.resolve(n_entries=big, storage="bfloat16")["storage"] == "bfloat16"
+    assert not options.resolve(n_entries=big, dtype="float32").get("storage")        # explicit dtype: exact CUDA-core path
+    assert not options.resolve(n_entries=big, n_gpus=2).get("storage")
+    with pytest.raises(TypeError):
+        options.resolve(n_entries=big, storrage="bfloat16")
+
+
 def test_library_loads_and_exports_every_declared_symbol():
     assert os.path.exists(LIB), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
     lib = ctypes.CDLL(LIB)
