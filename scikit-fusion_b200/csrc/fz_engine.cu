@@ -400,6 +400,9 @@ class Engine : public EngineBase {
                             // itself gets faster (0.69 -> 0.73 of the roofline) but the step does not -- the work it was sharing
                             // the SMs with still has to run (profiles/r02_bench_n4_{static,dynamic_tail}.log)
   DevBuf sched_ctr_;        // chunk counter of its dynamic tail
+  int reserve_sms_ = 0;     // SMs the persistent single-term kernel leaves free (FZ_RESERVE_SMS): the fp64 reductions, the
+                            // correction and the exchange kernels then run BESIDE the streamed product instead of delaying the
+                            // CTAs of the next launch (a one-CTA-per-SM kernel with 225 KB of shared memory shares its SMs with nothing)
   bool no_corr_ = false;    // FZ_NO_CORR=1 (studies / tests only): single-term kernel WITHOUT the first-order correction of M
   bool single_now_ = false; // this iteration's fused products use the single-term kernel (umma_fused1.cuh) + M correction
   // ---- FZ_TERMS_AUTO: which kernel may run is decided from measurements (gate_measure / gate_decide)
@@ -757,6 +760,7 @@ class Engine : public EngineBase {
     if (const char* oe = getenv("FZ_OBJ_EXACT")) obj_exact_ = (oe[0] == '1');
     if (const char* tl = getenv("FZ_TIMELINE")) timeline_ = (tl[0] == '1');
     if (const char* nd = getenv("FZ_DYN_SCHED")) dyn_sched_ = (nd[0] == '1') ? 1 : 0;
+    if (const char* rs = getenv("FZ_RESERVE_SMS")) reserve_sms_ = std::max(0, std::min(sms / 2, atoi(rs)));
     sched_ctr_.alloc(64);
     if (gs_terms_ != 2) fused_ = false;
     if (const char* na = getenv("FZ_NO_AUX")) use_aux_ = !(na[0] == '1');
@@ -1797,13 +1801,14 @@ class Engine : public EngineBase {
   // FZ_BF16X3: split the fp32 master of a relation (part 0) or one sign part of a constraint matrix (+1 / -1) into its bf16
   // planes.  A first pass finds out how many planes hold anything (0/1 data, ratings, small integers: one), so only those are
   // allocated and streamed.  Set-up step: synchronises.
+  unsigned plane_grid(int64_t rows) const { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(rows, 16ll * sm_count_)); }
   void build_planes(RelRec& r, PlaneSet& ps, int part, bool all_three, bool keep_one) {
     if (kDT != FZ_F32) FZ_THROW(FZ_ERR_UNSUPPORTED, "bf16 planes need the fp32 engine");
     DevBuf need;
     need.alloc(4 * sizeof(unsigned int));
     unsigned int h[4] = {0, 0, 0, 0};
     if (r.rows_loc > 0) {
-      planes_needed<<<nblk(r.rows_loc * r.cols, 256), 256>>>((const float*)r.data, r.ld, r.rows_loc, r.cols, part,
+      planes_needed<<<plane_grid(r.rows_loc), 256>>>((const float*)r.data, r.ld, r.rows_loc, r.cols, part,
                                                              need.template as<unsigned int>());
       ++launches;
       CUDA_OK(cudaGetLastError());
@@ -1820,7 +1825,7 @@ class Engine : public EngineBase {
     ps.stride = rows * ps.ld;
     ps.buf.alloc((size_t)n * ps.stride * 2);        // zeroed: pad columns and absent rows read as 0
     if (r.rows_loc > 0) {
-      split_planes<<<nblk(r.rows_loc * r.cols, 256), 256>>>((const float*)r.data, r.ld, ps.buf.template as<__nv_bfloat16>(), ps.ld,
+      split_planes<<<plane_grid(r.rows_loc), 256>>>((const float*)r.data, r.ld, ps.buf.template as<__nv_bfloat16>(), ps.ld,
                                                             ps.stride, n, r.rows_loc, r.cols, part);
       ++launches;
       CUDA_OK(cudaGetLastError());
@@ -1837,7 +1842,7 @@ class Engine : public EngineBase {
   // dfmc rewrote the unknown entries of the master (mask_zero / impute_masked): bring the planes up to date there
   void resplit_masked(RelRec& r, cudaStream_t st) {
     if (!r.x3 || r.mask == nullptr || r.rows_loc <= 0) return;
-    split_planes_masked<<<nblk(r.rows_loc * r.cols, 256), 256, 0, st>>>((const float*)r.data, r.ld, r.mask, r.mask_ld,
+    split_planes_masked<<<plane_grid(r.rows_loc), 256, 0, st>>>((const float*)r.data, r.ld, r.mask, r.mask_ld,
                                                                         r.pl.buf.template as<__nv_bfloat16>(), r.pl.ld, r.pl.stride, r.pl.n,
                                                                         r.rows_loc, r.cols);
     ++launches;
@@ -2311,7 +2316,7 @@ bool Engine<float>::product_AB_fused(RelRec& r, cudaStream_t st) {
     // persistent grid: one CTA per SM; three quarters of the (row group x column tile) units in equal static shares, the last
     // quarter in chunks handed out on demand (umma_fused1.cuh: F1Segments)
     const long long units = (long long)pairs * tiles;
-    const unsigned ctas = (unsigned)std::max<long long>(1, std::min<long long>(sm_count_, units));
+    const unsigned ctas = (unsigned)std::max<long long>(1, std::min<long long>(std::max(1, sm_count_ - reserve_sms_), units));
     q.dyn_chunk = 0;
     q.work_counter = nullptr;
     if (dyn_sched_ == 1 && units >= 16ll * ctas) {

@@ -887,47 +887,68 @@ __device__ __forceinline__ float plane_part(float v, int part) {
   if (part < 0) return v < 0.f ? -v : 0.f;
   return v;
 }
-// need[t] = 1 when plane t of the split holds a non-zero somewhere (integers, ratings, 0/1 data fit plane 0 alone)
-__global__ void planes_needed(const float* __restrict__ X, long long ld, long long rows, long long cols, int part,
-                              unsigned int* __restrict__ need) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * cols) return;
-  float v = plane_part(X[(idx / cols) * ld + (idx % cols)], part);
-  if (v != v || fabsf(v) > 3.3e38f) { need[3] = 1u; return; }        // non-finite entries cannot be split: refused by the caller
-  if (v != 0.f) need[0] = 1u;
-  v -= __bfloat162float(__float2bfloat16_rn(v));
-  if (v != 0.f) need[1] = 1u;
-  v -= __bfloat162float(__float2bfloat16_rn(v));
-  if (v != 0.f) need[2] = 1u;
+// need[t] = 1 when plane t of the split holds a non-zero somewhere (integers, ratings, 0/1 data fit plane 0 alone); need[3] = 1
+// on a non-finite entry.  One block walks whole rows (coalesced, no index division); the verdict of a block is folded in
+// shared memory and written once, so the four flags are not hammered by every thread.  grid = min(rows, a few waves).
+__global__ void __launch_bounds__(256)
+planes_needed(const float* __restrict__ X, long long ld, long long rows, long long cols, int part, unsigned int* __restrict__ need) {
+  unsigned int f = 0u;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* row = X + r * ld;
+    for (long long c = threadIdx.x; c < cols; c += blockDim.x) {
+      float v = plane_part(row[c], part);
+      if (v != v || fabsf(v) > 3.3e38f) { f |= 8u; continue; }      // non-finite entries cannot be split: refused by the caller
+      if (v != 0.f) f |= 1u;
+      v -= __bfloat162float(__float2bfloat16_rn(v));
+      if (v != 0.f) f |= 2u;
+      v -= __bfloat162float(__float2bfloat16_rn(v));
+      if (v != 0.f) f |= 4u;
+    }
+  }
+  __shared__ unsigned int sf;
+  if (threadIdx.x == 0) sf = 0u;
+  __syncthreads();
+  f = __reduce_or_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(&sf, f);
+  __syncthreads();
+  if (threadIdx.x < 4 && ((sf >> threadIdx.x) & 1u)) need[threadIdx.x] = 1u;
 }
-// P[t][r][c] = term t (t < n_planes); plane t starts at P + t * plane_stride, rows pitched to ldp (pad columns stay zero)
-__global__ void split_planes(const float* __restrict__ X, long long ld, __nv_bfloat16* __restrict__ P, long long ldp,
-                             long long plane_stride, int n_planes, long long rows, long long cols, int part) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * cols) return;
-  const long long r = idx / cols, c = idx % cols;
-  float v = plane_part(X[r * ld + c], part);
-  __nv_bfloat16* out = P + r * ldp + c;
-  for (int t = 0; t < n_planes; ++t) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    out[(long long)t * plane_stride] = h;
-    v -= __bfloat162float(h);
+// P[t][r][c] = term t (t < n_planes); plane t starts at P + t * plane_stride, rows pitched to ldp (pad columns stay zero).
+// grid = min(rows, a few waves) blocks, each walking whole rows.
+__global__ void __launch_bounds__(256)
+split_planes(const float* __restrict__ X, long long ld, __nv_bfloat16* __restrict__ P, long long ldp, long long plane_stride,
+             int n_planes, long long rows, long long cols, int part) {
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* row = X + r * ld;
+    __nv_bfloat16* out = P + r * ldp;
+    for (long long c = threadIdx.x; c < cols; c += blockDim.x) {
+      float v = plane_part(row[c], part);
+      for (int t = 0; t < n_planes; ++t) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        out[(long long)t * plane_stride + c] = h;
+        v -= __bfloat162float(h);
+      }
+    }
   }
 }
 // the same for the masked entries only (dfmc re-imputes them every iteration; the known entries never change)
-__global__ void split_planes_masked(const float* __restrict__ X, long long ld, const uint8_t* __restrict__ mask, long long mld,
-                                    __nv_bfloat16* __restrict__ P, long long ldp, long long plane_stride, int n_planes,
-                                    long long rows, long long cols) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * cols) return;
-  const long long r = idx / cols, c = idx % cols;
-  if (!mask[r * mld + c]) return;
-  float v = X[r * ld + c];
-  __nv_bfloat16* out = P + r * ldp + c;
-  for (int t = 0; t < n_planes; ++t) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    out[(long long)t * plane_stride] = h;
-    v -= __bfloat162float(h);
+__global__ void __launch_bounds__(256)
+split_planes_masked(const float* __restrict__ X, long long ld, const uint8_t* __restrict__ mask, long long mld,
+                    __nv_bfloat16* __restrict__ P, long long ldp, long long plane_stride, int n_planes, long long rows,
+                    long long cols) {
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* row = X + r * ld;
+    const uint8_t* mrow = mask + r * mld;
+    __nv_bfloat16* out = P + r * ldp;
+    for (long long c = threadIdx.x; c < cols; c += blockDim.x) {
+      if (!mrow[c]) continue;
+      float v = row[c];
+      for (int t = 0; t < n_planes; ++t) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        out[(long long)t * plane_stride + c] = h;
+        v -= __bfloat162float(h);
+      }
+    }
   }
 }
 // out[r] = sum over the columns of one sign part of X (fp64 accumulation): the rank-1 part of Theta+- G in the centred form

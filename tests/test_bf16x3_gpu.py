@@ -81,9 +81,11 @@ def test_integer_valued_relations_need_one_plane_only():
     assert abs(out["bfloat16x3"][2] - out["bfloat16"][2]) <= 4, (out["bfloat16x3"][2], out["bfloat16"][2])
 
 
-@pytest.mark.parametrize("storage,init", [("bfloat16x3", "random"), ("bfloat16x3", "random_vcol"), ("bfloat16", "random")])
-def test_ranks_above_64_on_the_tensor_cores(storage, init):
-    """Two-pass kernels over 64-column blocks of the factor operand (ranks 96 / 130 / 64)."""
+@pytest.mark.parametrize("dtype,storage,init", [("float32", "bfloat16x3", "random"), ("float32", "bfloat16x3", "random_vcol"),
+                                                ("float32", "bfloat16", "random"), ("float64", None, "random")])
+def test_ranks_above_64(dtype, storage, init):
+    """Ranks 96 / 130 / 64: two-pass tensor-core kernels over 128-column blocks of the factor operand, and the k x k chain
+    tiled through shared memory (csrc/fz_chain.cuh: block_mm); the float64 engine checks that chain to 1e-8."""
     from skfusion.fusion import solver
     types, ranks, R = _graph((520, 392, 300), (96, 130, 64), 3)
     if storage == "bfloat16":
@@ -92,9 +94,25 @@ def test_ranks_above_64_on_the_tensor_cores(storage, init):
         warnings.simplefilter("ignore")
         Go, So = oracle.dfmf(R, {}, types, ranks, max_iter=12, init_type=init, random_state=np.random.RandomState(0))
         G, S = solver.dfmf(R, {}, types, ranks, max_iter=12, init_type=init, random_state=np.random.RandomState(0),
-                           dtype="float32", storage=storage)
-    tol = (1e-4, 1e-3) if init == "random" else (1e-3, 5e-3)
+                           dtype=dtype, storage=storage)
+    tol = (1e-8, 1e-8) if dtype == "float64" else ((1e-4, 1e-3) if init == "random" else (1e-3, 5e-3))
     _check(Go, So, G, S, types, *tol)
+    if dtype == "float64":      # the trace-form objective (fz_objective) runs the same tiled k x k products
+        from skfusion import _capi
+        from test_objective_gpu import _engine
+        sizes = oracle.count_objects(R)
+        G0 = oracle.initialize(types, sizes, ranks, {}, "random", np.random.RandomState(0))
+        hist = []
+        oracle.dfmf(R, {}, types, ranks, max_iter=3, G0=G0, compute_err=True, history=hist)
+        eng, tid, rid = _engine(R, types, ranks, G0, dtype)
+        try:
+            got = []
+            for _ in range(3):
+                eng.iterate(_capi.FZ_DFMF, 1)
+                got.append(eng.objective(len(rid))[0])
+            np.testing.assert_allclose(got, hist, rtol=1e-9)
+        finally:
+            eng.close()
 
 
 @pytest.mark.parametrize("terms", [2, "auto"])
