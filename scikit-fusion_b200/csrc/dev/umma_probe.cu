@@ -632,6 +632,18 @@ static int main_fused1(int nbench, double sustain, int csplit) {
 
 int main(int argc, char** argv) {
   setvbuf(stdout, nullptr, _IONBF, 0);
+  if (argc > 1 && argv[1][0] == 'b') {   // timing only of the single-term kernel as compiled (geometry study):  b <n> <seconds> <ctas>
+    const int n = argc > 2 ? atoi(argv[2]) : 36864;
+    const double sustain = argc > 3 ? atof(argv[3]) : 2.0;
+    const int ctas = argc > 4 ? atoi(argv[4]) : 148;
+    printf("geometry: %d row blocks per group, %d relation stages, %d B of flush staging, %d B of shared memory\n", kF1Blocks, kF1RStages,
+           kF1StageBytes, kF1SmemBytes);
+    g_sustain_s = 0;
+    for (int probe : {0, 1, 7}) bench_fused1(n, probe, ctas);
+    g_sustain_s = sustain;
+    for (int probe : {0, 1}) bench_fused1(n, probe, ctas);
+    return 0;
+  }
   if (argc > 1 && argv[1][0] == '1') return main_fused1(argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atof(argv[3]) : 0.0, argc > 4 ? atoi(argv[4]) : 148);
   if (argc > 1 && argv[1][0] == 'm') {   // single-term B-product (the fp16 variant of this probe hit an illegal instruction:
     int fails = 0;                       //  bf16 A x fp16 B is not a legal kind::f16 combination, profiles/r01b_mixed_format_probe.log)

@@ -42,15 +42,34 @@ struct Fused1Params {
   int probe;            // developer probe only (wrong results): bit0 no reductions, bit1 no B MMAs, bit2 no A MMAs
 };
 
+// Shared-memory geometry (compile-time; the probe csrc/dev/umma_probe.cu is built with each candidate):
+//   FZ_F1_BLOCKS   128-row blocks per row group = A accumulators in TMEM = resident Gs_i tiles; the B partial of a column
+//                  tile is flushed once per FZ_F1_BLOCKS relation tiles
+//   FZ_F1_RSTAGES  relation tiles (32 KB each) in flight per SM
+//   FZ_F1_STAGING  flush staging: 32768 = both 32-column halves of a 128 x 64 fp32 partial at once, 16384 = one half
+//                  after the other through the same 4 KB per warp
+#ifndef FZ_F1_BLOCKS
+#define FZ_F1_BLOCKS 4
+#endif
+#ifndef FZ_F1_RSTAGES
+#define FZ_F1_RSTAGES 3
+#endif
+#ifndef FZ_F1_STAGING
+#define FZ_F1_STAGING 32768
+#endif
 constexpr int kF1Threads = 224;   // warp 0: R producer | 1: MMA | 2..5: epilogue | 6: Gs producer
-constexpr int kF1Blocks = 4;      // 128-row blocks per row group
+constexpr int kF1Blocks = FZ_F1_BLOCKS;      // 128-row blocks per row group
 constexpr int kF1Tile = 128;
-constexpr int kF1RStages = 3;
+constexpr int kF1RStages = FZ_F1_RSTAGES;
 constexpr int kF1GjSlots = 2;
 constexpr int kF1TileBytes = kF1Tile * kF1Tile * 2;   // 32 KB relation tile
 constexpr int kF1GBytes = kF1Tile * 64 * 2;           // 16 KB: 128 rows x 64 columns of Gs (one term)
-constexpr int kF1StageBytes = 32768;                  // flush staging: 4 warps x 2 x (32 rows x 32 fp32)
+constexpr int kF1StageBytes = FZ_F1_STAGING;          // flush staging: 4 warps x (2 or 1) x (32 rows x 32 fp32)
+constexpr bool kF1HalfStaging = kF1StageBytes < 32768;
 constexpr int kF1SmemBytes = kF1RStages * kF1TileBytes + kF1GjSlots * kF1GBytes + kF1StageBytes + kF1Blocks * kF1GBytes + 1024 + 256;
+static_assert(kF1StageBytes == 32768 || kF1StageBytes == 16384, "staging holds one or both halves of a partial");
+static_assert(kF1Blocks >= 1 && kF1Blocks <= 4, "A accumulators occupy TMEM columns [0, 64 * blocks), B from 256");
+static_assert(kF1SmemBytes <= 227 * 1024, "shared memory budget of one CTA per SM");
 
 // Work of one launch = (row groups of 512 rows) x (128-column tiles), flattened row-group-major into "units" of one column
 // tile of one row group.  The first three quarters of the units are partitioned STATICALLY: CTA b of the persistent grid owns
@@ -277,7 +296,7 @@ umma_fused1_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16
     const int quarter = warp & 3;
     const int lrow = quarter * 32 + lane;                         // TMEM lane = row of the accumulator tile
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint8_t* my_stage = fl_st + quarter * 8192;                   // 2 x (32 rows x 128 B), 128B-swizzled like the reduce boxes
+    uint8_t* my_stage = fl_st + quarter * (kF1StageBytes / 4);    // 2 (or 1) x (32 rows x 128 B), 128B-swizzled like the reduce boxes
     const bool skip_red = (p.probe & 1) != 0;
     const bool b_tma = (p.tma_flush & 1) != 0, a_tma = (p.tma_flush & 2) != 0;
     bool staged = false;                                          // this warp has reduces in flight that read its staging
@@ -297,7 +316,30 @@ umma_fused1_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bacc_empty[gs]);                          // TMEM reads done: hand the buffer back to the MMA warp
         if (skip_red) continue;
-        if (b_tma) {
+        if (b_tma && kF1HalfStaging) {
+          // one 32-column half after the other through the warp's single 4 KB box
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && p.k_b <= 32) break;
+            if (staged) {
+              if (ptx::elect_one()) ptx::tma_wait_read_all();       // earlier reduces have read the staging
+              __syncwarp();
+            }
+            const float* v = h == 0 ? v0 : v1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (ptx::elect_one()) {
+              ptx::tma_reduce_add_2d(&tmB, my_stage, 32 * h, brow0);
+              ptx::tma_commit_group();
+            }
+            __syncwarp();
+            staged = true;
+          }
+        } else if (b_tma) {
           if (staged) {
             if (ptx::elect_one()) ptx::tma_wait_read_all();         // earlier reduces have read the staging
             __syncwarp();
@@ -355,7 +397,30 @@ umma_fused1_kernel(const __grid_constant__ CUtensorMap tmR,    // relation, bf16
             v1[i] = (32 + i < p.k_a) ? fmaf(rs, __ldg(p.cj + 32 + i), v1[i]) : v1[i];
           }
         }
-        if (a_tma) {
+        if (a_tma && kF1HalfStaging) {
+          const int arow0 = r0 + t * kF1Tile + quarter * 32;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && p.k_a <= 32) break;
+            if (staged) {
+              if (ptx::elect_one()) ptx::tma_wait_read_all();
+              __syncwarp();
+            }
+            const float* v = h == 0 ? v0 : v1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (ptx::elect_one()) {
+              ptx::tma_reduce_add_2d(&tmA, my_stage, 32 * h, arow0);   // rows beyond n_rows / columns beyond k_a are clipped
+              ptx::tma_commit_group();
+            }
+            __syncwarp();
+            staged = true;
+          }
+        } else if (a_tma) {
           if (staged) {
             if (ptx::elect_one()) ptx::tma_wait_read_all();
             __syncwarp();
