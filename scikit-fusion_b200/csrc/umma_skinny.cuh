@@ -89,13 +89,15 @@ umma_skinny_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Both issuing roles run as WHOLE, converged warps with one elected lane per step: under a divergent `if (lane == 0)` ptxas
+  // wraps every TMA / tcgen05 instruction in a ~100-cycle waterfall loop (csrc/dev/mma_pace.cu).
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % Cfg::kStages;
+      const uint32_t ph = (kb / Cfg::kStages) & 1;
+      ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+      if (ptx::elect_one()) {
         uint8_t* xs = smem + s * Cfg::kStageBytes;
         uint8_t* gs = xs + Cfg::kStageX;
         const int k0 = k_begin + kb * kSkBK;
@@ -114,16 +116,17 @@ umma_skinny_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                            p.g_col0 + (ch / p.chunks_per_term) * p.g_term_stride + (ch % p.chunks_per_term) * 64, p.g_row0 + k0,
                            ptx::kEvictLast);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kSkBM, N, kTransX, true);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
-        ptx::tc_fence_after();
+    constexpr uint32_t idesc = ptx::idesc_bf16_f32(kSkBM, N, kTransX, true);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % Cfg::kStages;
+      const uint32_t ph = (kb / Cfg::kStages) & 1;
+      ptx::mbar_wait(&full_bar[s], ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
         const uint32_t xs = ptx::smem_u32(smem + s * Cfg::kStageBytes);
         const uint32_t gs = xs + Cfg::kStageX;
 #pragma unroll
@@ -136,8 +139,10 @@ umma_skinny_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
         ptx::umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
       }
-      ptx::umma_commit(tmem_full_bar);    // accumulator complete
+      __syncwarp();
     }
+    if (ptx::elect_one()) ptx::umma_commit(tmem_full_bar);    // accumulator complete
+    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
