@@ -117,7 +117,9 @@ def cpu_arm(n_workload, budget_s=150.0, sizes=(4096, 8192, 16384), max_iters=5):
     limiter, threads, thread_desc = _blas_threads()
     run, kind = _reference_dfmf()
     points = []
-    for n_s in sizes:
+    queue = list(sizes)
+    while queue:
+        n_s = queue.pop(0)
         left = budget_s - (time.perf_counter() - t_begin)
         est = points[-1]["s_per_it"] * (float(n_s) / points[-1]["n"]) ** 2 if points else 0.0
         iters = max_iters
@@ -125,6 +127,12 @@ def cpu_arm(n_workload, budget_s=150.0, sizes=(4096, 8192, 16384), max_iters=5):
             iters = int(min(max_iters, (left - 0.25 * est) // max(est, 1e-9)))     # 0.25 est: generating the inputs
         need_b = 10.0 * n_s * n_s * 8 * 2.5
         if points and (iters < 2 or need_b > psutil.virtual_memory().available):
+            # this size does not fit the time or the host memory left: a fit wants at least three points (a residual), so
+            # fall back to a size half way to it instead of stopping at two
+            mid = ((points[-1]["n"] + n_s) // 2 // 1024) * 1024
+            if len(points) < 3 and mid > points[-1]["n"]:
+                queue = [mid]
+                continue
             break
         types, ranks, R = _cpu_graph(n_s)
         stamps = []
