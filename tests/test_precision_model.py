@@ -46,3 +46,34 @@ def test_two_split_terms_meet_the_stated_tolerance_on_ill_conditioned_seeds():
 def test_one_bf16_term_does_not():
     g, s = _errors("random_c", "A bf16x1 / B bf16x1")
     assert s > 5e-3, (g, s)
+
+
+def test_three_bf16_planes_hold_a_float32_exactly():
+    """The exact tensor-core form (storage='bfloat16x3', csrc/fz_kernels.cuh: split_planes): a float32 is the sum of three
+    round-to-nearest bf16 terms of its running residual, whatever its magnitude or sign -- and data with few significant
+    bits (0/1, ratings, small integers, bf16 values) need fewer planes, which the engine then neither stores nor streams."""
+    rs = np.random.RandomState(0)
+    x = np.concatenate([rs.rand(20000), rs.randn(20000) * 1e-3, rs.randn(20000) * 1e6, -rs.rand(1000) * 3.3e38 * 0.5,
+                        rs.rand(1000) * 1e-30, [0.0, 1.0, -1.0, 1 / 3, 16777215.0, 1.1754944e-38]]).astype(np.float32)
+    res = x.astype(np.float64)
+    total = np.zeros_like(res)
+    for _ in range(3):
+        term = ps.bf16(res.astype(np.float32))          # the residuals are float32-representable: the cast is exact
+        assert np.array_equal(res.astype(np.float32).astype(np.float64), res)
+        total += term
+        res = res - term
+    assert np.array_equal(total, x.astype(np.float64)) and not res.any()
+
+    def planes_needed(v):
+        r = np.asarray(v, dtype=np.float32).astype(np.float64)
+        need = 0
+        for t in range(3):
+            if r.any():
+                need = t + 1
+            r = r - ps.bf16(r.astype(np.float32))
+        return need
+    assert planes_needed(rs.randint(0, 2, 1000)) == 1                       # 0/1 relations
+    assert planes_needed(rs.randint(0, 11, 1000) * 0.5) == 1                # ratings in half steps
+    assert planes_needed(rs.randint(0, 256, 1000)) == 1                     # 8 significant bits
+    assert planes_needed(rs.randint(0, 60000, 1000)) == 2                   # 16 significant bits
+    assert planes_needed(rs.rand(1000)) == 3
