@@ -165,3 +165,38 @@ def test_host_layer_matches_reference_dfmc_and_transform_in_process():
     for a, b in zip(out["ref"][2], out["own"][2]):
         assert rel_fro(a, b) < 1e-10
     assert rel_fro(out["ref"][3], out["own"][3]) < 1e-11
+
+
+@pytest.mark.parametrize("which", ["wide_ranks", "constraints", "completion"])
+def test_oracle_equals_reference_on_the_graphs_of_the_exact_planes_tests(which):
+    """tests/test_bf16x3_gpu.py compares the tensor-core paths with the oracle on graphs of a few hundred objects with ranks
+    above 64, constraint matrices of both signs and a masked relation: pin the oracle to the real reference on those very
+    inputs (same seeds, fewer iterations)."""
+    import test_bf16x3_gpu as x3
+    r_dfmf, r_dfmc, _, _ = ref.functions()
+    Theta, M = {}, None
+    if which == "wide_ranks":
+        types, ranks, R = x3._graph((520, 392, 300), (96, 130, 64), 3)
+    elif which == "constraints":
+        types, ranks, R = x3._graph((520, 392, 300), (40, 64, 24), 7)
+        rs = np.random.RandomState(11)
+        th0 = cases._sparse_sym_constraint(rs, 520, density=0.02, scale=0.1).astype(np.float32).astype(np.float64)
+        th1 = -np.where(rs.rand(392, 392) < 0.03, 0.005, 0.0).astype(np.float32).astype(np.float64)
+        Theta = {("t0", "t0"): [th0], ("t1", "t1"): [th1, th1.T.copy()]}
+    else:
+        types, ranks, R = x3._graph((392, 520, 136), (24, 32, 8), 9)
+        M = {("t0", "t1"): [np.random.RandomState(2).rand(392, 520) < 0.3], ("t0", "t2"): [None], ("t1", "t2"): [None]}
+    kw = dict(obj_types=types, obj_type2rank=ranks, max_iter=4, init_type="random")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if M is not None:
+            G1, S1 = r_dfmc(R, M, Theta, random_state=np.random.RandomState(0), **kw)
+            G2, S2 = oracle.dfmc(R, M, Theta, random_state=np.random.RandomState(0), **kw)
+        else:
+            G1, S1 = r_dfmf(R, Theta, random_state=np.random.RandomState(0), **kw)
+            G2, S2 = oracle.dfmf(R, Theta, random_state=np.random.RandomState(0), **kw)
+    for key in G1:
+        assert rel_fro(G1[key], G2[key]) < 1e-11
+    for key in S1:
+        for a, b in zip(S1[key], S2[key]):
+            assert rel_fro(a, b) < 1e-9
